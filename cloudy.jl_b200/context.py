@@ -1,0 +1,61 @@
+"""Device context handling for the host mirror."""
+import ctypes as C
+import threading
+
+from . import _lib as L
+
+_default = None
+_lock = threading.Lock()
+
+
+class Context:
+    """Owns a ``cloudy_ctx`` (one device, one stream)."""
+
+    def __init__(self, device: int = 0, stream=None):
+        lib = L.load()
+        self._lib = lib
+        h = C.c_void_p()
+        L.check(lib.cloudy_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.handle = h
+        self.device = device
+        self.config = None  # the CoalescenceData / model parameters currently on the device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.cloudy_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        L.check(self._lib.cloudy_sync(self.handle))
+
+    def set_lanes(self, lanes: int):
+        L.check(self._lib.cloudy_set_lanes(self.handle, int(lanes)))
+
+    def launch_count(self) -> int:
+        v = C.c_int64()
+        L.check(self._lib.cloudy_launch_count(self.handle, C.byref(v)))
+        return v.value
+
+    def error_count(self) -> int:
+        v = C.c_int64()
+        L.check(self._lib.cloudy_error_count(self.handle, C.byref(v)))
+        return v.value
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double()
+        L.check(self._lib.cloudy_measure_fp64_peak(self.handle, C.byref(v)))
+        return v.value
+
+
+def default_context() -> Context:
+    global _default
+    with _lock:
+        if _default is None:
+            _default = Context(0)
+        return _default

@@ -1,0 +1,1418 @@
+// libcloudy_b200.so — batched Cloudy.jl coalescence / sedimentation tendencies on B200 (sm_100a).
+//
+// One CUDA kernel template (rhs_kernel) evaluates, for a tile of parcels (box model) or column cells
+// (rainshaft), everything the reference's ODE right-hand side does per parcel
+//   test/examples/utils/box_model_helpers.jl:29-53   (rhs_coal!)
+//   test/examples/utils/rainshaft_helpers.jl:47-88   (make_rainshaft_rhs)
+//   src/Sources/Coalescence.jl:115-455               (get_coal_ints, AnalyticalCoalStyle)
+//   src/ParticleDistributions/ParticleDistributions.jl:456-612, :698-710
+//   src/Sources/Sedimentation.jl:22-37
+// and, when asked, applies one SSPRK33 stage update in the same pass (state read once, written once).
+//
+// Execution shape: LANES (4..32) lanes of a warp cooperate on one parcel.  Quadrature nodes of the
+// reference's log-spaced end-corrected Simpson rule are strided over the lanes; the T = M'(M'+1)/2
+// truncated-moment accumulators are combined with an xor-butterfly of warp shuffles.  Per node ONE
+// incomplete gamma function is evaluated at the top order (fixed-trip Horner series or fixed-depth
+// continued fraction, per-parcel coefficient tables in shared memory) and the lower orders follow
+// from the downward recurrence gamma(a,z) = (gamma(a+1,z) + z^a e^-z)/a.  The polynomial-kernel
+// contraction (Q/R/S) runs one output moment per lane from shared memory.  FP64 CUDA cores only.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/cloudy_b200.h"
+#include "special.cuh"
+
+namespace cloudy {
+
+// ------------------------------------------------------------------------------------------------
+// device-side configuration (kernel parameter, lives in the constant bank)
+// ------------------------------------------------------------------------------------------------
+constexpr int MAXN = CLOUDY_MAX_MODES;
+constexpr int MAXP = CLOUDY_MAX_P;
+constexpr int MAXM = MAXP + 2;
+constexpr int MAXSLOT = CLOUDY_MAX_SLOTS;
+constexpr int MAXT = MAXM * (MAXM + 1) / 2;  // 28
+
+struct DevConfig {
+    int N, P, M, nslots;
+    int kind[MAXN], nprog[MAXN], slot0[MAXN];
+    int slot_mode[MAXSLOT], slot_order[MAXSLOT];
+    int thr_style, n_mom_max;
+    int n2d[MAXN], Mp[MAXN];       // Mp = min(M, n2d): orders 0..Mp-1 carry truncated integrals
+    int quad[MAXN];                // 1: Gamma/Exponential mode with finite threshold, not last → node loop
+    int mono_thr[MAXN];            // 1: Monodisperse mode with finite threshold, not last → closed form
+    int n_bins[MAXN], tab_off[MAXN];
+    int tab_total;                 // doubles of grid tables to stage in shared memory
+    int n_vel, nz;
+    double c[MAXN][MAXN][MAXP][MAXP];
+    double thr[MAXN];
+    double norm[MAXSLOT];
+    double k_lo, k_hi;
+    double velv[CLOUDY_MAX_VEL], velb[CLOUDY_MAX_VEL];  // v*norms[2]^beta, beta
+    double inv_dz_unused, dz;
+    const double* tab;  // device: per quad mode i at tab_off[i]: XJ[n] ELL[n] TMX[n] LZ[n] W[M][n]
+};
+
+struct KArgs {
+    const double* u_in;   // state the RHS is evaluated at
+    const double* u_n;    // u^n for stages 2,3 (nullptr otherwise)
+    double* out;          // tendency, flux or stage result
+    double* clip_back;    // rainshaft tendency call: clipped state written back (nullptr otherwise)
+    long long n;          // parcels / cells
+    long long s_in, s_n, s_out, s_clip;  // SoA strides (doubles)
+    double cn, ci, cf, dt, div;          // out = (cn*u_n + ci*u_in + cf*(dt*f))/div ; tend_only: out = f
+    int tend_only;
+    int flux_only;        // out = sedimentation flux (rainshaft_helpers.jl:77)
+    int params_in;        // u_in holds distribution parameters (n, θ|μ[, k|σ]) instead of moments; output not de-normalised
+    unsigned long long* err_count;
+};
+
+enum { MODEL_BOX = 0, MODEL_RAINSHAFT = 1 };
+
+template <int LANES>
+struct Shape {
+    static constexpr int kThreads = (LANES >= 8) ? 256 : 32 * LANES;
+    static constexpr int kGroups = kThreads / LANES;  // parcels per tile (<= 32)
+};
+
+// per-group shared-memory record (doubles)
+constexpr int PAR_N = 0, PAR_TH = 1, PAR_K = 2, PAR_INVTH = 3, PAR_LOGTH = 4, PAR_IGK2 = 5, PAR_GK = 6, PAR_STRIDE = 8;
+constexpr int TAB_CT = 0;                            // series coefficients c_n, n = 0..63
+constexpr int TAB_CF = 64;                           // cf numerators n(a-n), n = 1..16 at [64+n]
+constexpr int TAB_IA = TAB_CF + kCfMaxDepth + 1;     // 1/(k+p), p = 0..5
+constexpr int TAB_LEN = TAB_IA + MAXM;               // 88
+constexpr int TAB_STRIDE = TAB_LEN + 1;              // odd → groups of a warp hit different banks
+
+struct GroupLayout {
+    int mom, par, F, tab, in, un, out, flux, total;
+};
+__host__ __device__ inline GroupLayout group_layout(int N, int M, int nslots, bool rain) {
+    GroupLayout g;
+    int o = 0;
+    g.mom = o; o += N * M;
+    g.par = o; o += N * PAR_STRIDE;
+    g.F = o; o += (N > 1 ? (N - 1) : 1) * MAXT;
+    g.tab = o; o += TAB_STRIDE;
+    g.in = o; o += nslots;
+    g.un = o; o += nslots;
+    g.out = o; o += nslots;
+    g.flux = o; o += rain ? nslots : 0;
+    g.total = o | 1;  // odd stride
+    return g;
+}
+
+__device__ __forceinline__ int tri_index(int p1, int p2, int Mcols) {  // p1 <= p2 < Mcols, row-major upper triangle
+    return p1 * Mcols - (p1 * (p1 - 1)) / 2 + (p2 - p1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// distribution parameters from normalised moments — ParticleDistributions.jl:456-541 — and the
+// moment matrix row of one mode — Coalescence.jl:187-198 / ParticleDistributions.jl:177-207
+// ------------------------------------------------------------------------------------------------
+struct ModeParams {
+    double n, a, b;  // (n, θ, k) or (n, μ, σ); b = 1 for Exponential/Monodisperse
+    int invalid;
+};
+
+__device__ inline ModeParams params_from_moments(int kind, double m0, double m1, double m2, double lo, double hi,
+                                                 double lo2 = kEps, double hi2 = INFINITY) {
+    ModeParams r;
+    r.invalid = 0;
+    if (kind == CLOUDY_GAMMA) {
+        if (m0 > kEps && m1 > kEps) {
+            r.n = m0;
+            double mean = m1 / m0;
+            double k = jl_max(lo, jl_min(hi, mean / (m2 / m1 - mean)));
+            r.b = k;
+            r.a = mean / k;
+        } else {
+            r.n = 0.0; r.a = 1.0; r.b = 1.0;
+        }
+    } else if (kind == CLOUDY_LOGNORMAL) {
+        if (m0 > kEps && m1 > kEps && m2 > kEps) {
+            // lo/hi clamp μ, lo2/hi2 clamp σ (reference defaults (-Inf, Inf), (eps, Inf))
+            double mu = jl_max(lo, jl_min(hi, log(m1 * m1 / (m0 * sqrt(m0)) / sqrt(m2))));
+            double arg = log(m0 * m2 / (m1 * m1));
+            if (arg < 0.0) r.invalid = 1;  // the reference throws a DomainError here (:498)
+            double sg = jl_max(lo2, jl_min(hi2, sqrt(arg)));
+            r.a = mu;
+            r.b = sg;
+            r.n = m1 / exp(mu + 0.5 * sg * sg);
+        } else {
+            r.n = 0.0; r.a = 1.0; r.b = 1.0;
+        }
+    } else {  // Exponential, Monodisperse
+        if (m0 > kEps && m1 > kEps) {
+            r.n = m0; r.a = m1 / m0; r.b = 1.0;
+        } else {
+            r.n = 0.0; r.a = 1.0; r.b = 1.0;
+        }
+    }
+    return r;
+}
+
+// moment(dist, q) for real q — ParticleDistributions.jl:177-207
+__device__ inline double moment_real(int kind, double n, double a, double b, double q) {
+    switch (kind) {
+        case CLOUDY_EXPONENTIAL: return n * pow(a, q) * tgamma(q + 1.0);
+        case CLOUDY_GAMMA: return n * pow(a, q) * tgamma(q + b) / tgamma(b);
+        case CLOUDY_MONODISPERSE: return n * pow(a, q);
+        default: return n * exp(q * a + q * q * b * b / 2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// node loop: T accumulators of  sum_j W[p1][j] * g_j * gamma(k+p2, z_j),  p1 <= p2 < Mp
+// ------------------------------------------------------------------------------------------------
+template <int MPMAX, int LANES>
+__device__ __forceinline__ void node_integrals(double (&acc)[MPMAX * (MPMAX + 1) / 2], const double* __restrict__ tb, int nb, int M,
+                                               int Mp, double k, double inv_th, double log_th, double gam_top,
+                                               const double* __restrict__ gtab, int deg_w, int cfd, int lane) {
+    constexpr int T = MPMAX * (MPMAX + 1) / 2;
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[t] = 0.0;
+    const double* XJ = tb;
+    const double* ELL = tb + nb;
+    const double* TMX = tb + 2 * nb;
+    const double* LZ = tb + 3 * nb;
+    const double* W = tb + 4 * nb;
+    const double a_top = k + (double)(Mp - 1);
+    const double ser_lim = a_top + (double)kSeriesMargin;
+    const int rounds = (nb + LANES - 1) / LANES;
+    for (int r = 0; r < rounds; ++r) {
+        int j = r * LANES + lane;
+        const bool valid = j < nb;
+        j = valid ? j : nb - 1;
+        const double u = XJ[j] * inv_th;
+        const double g = exp(fma(k, ELL[j] - log_th, -u));      // (x_j/θ)^k e^{-x_j/θ}
+        const double z = TMX[j] * inv_th;                        // (x_th - x_j)/θ
+        const double E = exp(fma(k, LZ[j] - log_th, -z));        // z^k e^{-z}
+        double zp[MPMAX];
+        zp[0] = 1.0;
+#pragma unroll
+        for (int p = 1; p < MPMAX; ++p) zp[p] = zp[p - 1] * z;
+        double Etop = E;
+#pragma unroll
+        for (int p = 1; p < MPMAX; ++p) Etop = (p < Mp) ? Etop * z : Etop;  // E * z^(Mp-1)
+        const bool use_ser = z < ser_lim;
+        double gam[MPMAX];
+        double gtop = 0.0;
+        if (__any_sync(0xffffffffu, use_ser)) {
+            double s = gtab[TAB_CT + deg_w];
+#pragma unroll 4
+            for (int n = deg_w - 1; n >= 0; --n) s = fma(s, z, gtab[TAB_CT + n]);
+            gtop = Etop * s;
+        }
+        if (__any_sync(0xffffffffu, !use_ser)) {
+            const double zc = fmin(z, 256.0);  // beyond this the upper function is < 1e-80 of Gamma(a)
+            double b = zc + 1.0 - a_top;
+            double Pm = 1.0, Pc = b, Qm = 0.0, Qc = 1.0;
+            for (int n = 1; n <= cfd; ++n) {
+                const double an = -gtab[TAB_CF + n];  // -n(n-a) = n(a-n) negated
+                b += 2.0;
+                const double Pn = fma(b, Pc, an * Pm);
+                const double Qn = fma(b, Qc, an * Qm);
+                Pm = Pc; Pc = Pn; Qm = Qc; Qc = Qn;
+            }
+            // E_top(zc): only differs from Etop when z > 256, where both are negligible
+            const double up = Etop * (Qc / Pc);
+            if (!use_ser) gtop = gam_top - up;
+        }
+        // downward recurrence to the lower orders
+#pragma unroll
+        for (int p = MPMAX - 1; p >= 0; --p) {
+            if (p == Mp - 1) gam[p] = gtop;
+            else if (p < Mp - 1) gam[p] = (gam[p + 1] + E * zp[p]) * gtab[TAB_IA + p];
+            else gam[p] = 0.0;
+        }
+        const double gv = valid ? g : 0.0;
+        int t = 0;
+#pragma unroll
+        for (int p1 = 0; p1 < MPMAX; ++p1) {
+            const double wg = (p1 < Mp) ? W[p1 * nb + j] * gv : 0.0;
+#pragma unroll
+            for (int p2 = p1; p2 < MPMAX; ++p2) {
+                acc[t] = fma(wg, gam[p2], acc[t]);
+                ++t;
+            }
+        }
+    }
+    // butterfly over the LANES of the group
+#pragma unroll
+    for (int off = LANES / 2; off > 0; off >>= 1) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], off);
+    }
+}
+
+// F_k[x][y] accessor — Coalescence.jl:200-244
+__device__ __forceinline__ double F_entry(const DevConfig& cfg, const double* mom_k, const double* par_k, const double* F_k, int k,
+                                          int x, int y) {
+    const double mm = mom_k[x] * mom_k[y];
+    if (mm < kEps || x >= cfg.n2d[k] || y >= cfg.n2d[k]) return 0.0;
+    if (cfg.quad[k]) {
+        const int lo = min(x, y), hi = max(x, y);
+        return F_k[tri_index(lo, hi, cfg.Mp[k])];
+    }
+    if (cfg.mono_thr[k]) {  // ParticleDistributions.jl:557-564
+        const double th = par_k[PAR_TH], n = par_k[PAR_N];
+        double h = 0.0;
+        if (th < cfg.thr[k] / 2) {
+            h = n * n;
+            for (int i = 0; i < x + y; ++i) h *= th;
+        }
+        return jl_min(mm, h);
+    }
+    return mm;  // last mode or infinite threshold
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int MPMAX, int LANES, int MODEL>
+__global__ void __launch_bounds__(Shape<LANES>::kThreads) rhs_kernel(const __grid_constant__ DevConfig cfg, const KArgs args) {
+    constexpr int G = Shape<LANES>::kGroups;
+    constexpr int THREADS = Shape<LANES>::kThreads;
+    constexpr bool RAIN = (MODEL == MODEL_RAINSHAFT);
+    constexpr int T = (MPMAX > 0) ? MPMAX * (MPMAX + 1) / 2 : 1;
+    extern __shared__ double smem[];
+
+    const int N = cfg.N, P = cfg.P, M = cfg.M, nslots = cfg.nslots;
+    const int tid = threadIdx.x;
+    const int lane = tid % LANES;
+    const int grp = tid / LANES;
+    const GroupLayout L = group_layout(N, M, nslots, RAIN);
+
+    // block-level shared data: kernel tensors (compact [j][k][a][b]), grid tables, then group records
+    double* sC = smem;
+    double* sTab = sC + N * N * P * P;
+    double* sGroups = sTab + cfg.tab_total;
+    double* sHaloFlux = sGroups + (size_t)G * L.total;  // rainshaft: flux of the cell above the tile
+    double* my = sGroups + (size_t)grp * L.total;
+
+    for (int i = tid; i < N * N * P * P; i += THREADS) {
+        int b = i % P, a = (i / P) % P, kk = (i / (P * P)) % N, jj = i / (P * P * N);
+        sC[i] = cfg.c[jj][kk][a][b];
+    }
+    for (int i = tid; i < cfg.tab_total; i += THREADS) sTab[i] = cfg.tab[i];
+
+    const long long n_tiles = (args.n + G - 1) / G;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long p0 = tile * G;
+        __syncthreads();  // previous tile fully consumed (and staging done on the first pass)
+        // ---- load phase (coalesced: consecutive threads → consecutive parcels of one slot) ----
+        const int n_load = RAIN ? G + 1 : G;
+        for (int i = tid; i < nslots * n_load; i += THREADS) {
+            const int s = i / n_load, g = i % n_load;
+            const long long p = p0 + g;
+            double v = 0.0, vn = 0.0;
+            bool in_range = p < args.n;
+            if (RAIN && g == G) in_range = in_range && (p % cfg.nz != 0);  // halo must be in the same column
+            if (in_range) {
+                v = args.u_in[s * args.s_in + p];
+                if (RAIN) v = (v < 0.0) ? 0.0 : v;  // rainshaft_helpers.jl:52
+                if (args.u_n != nullptr && g < G) {
+                    vn = args.u_n[s * args.s_n + p];
+                    if (RAIN) vn = (vn < 0.0) ? 0.0 : vn;
+                }
+                if (RAIN && args.clip_back != nullptr && g < G) args.clip_back[s * args.s_clip + p] = v;
+            }
+            if (g < G) {
+                double* rec = sGroups + (size_t)g * L.total;
+                rec[L.in + s] = v;
+                rec[L.un + s] = vn;
+            } else {
+                sHaloFlux[nslots + s] = v;  // halo cell's moments, staged after its flux slots
+            }
+        }
+        __syncthreads();
+        // ---- setup phase: lane ↔ mode ----
+        const int n_cells = RAIN ? 2 : 1;  // own cell; rainshaft group 0 also does the halo cell
+        for (int cell = 0; cell < n_cells; ++cell) {
+            if (cell == 1 && grp != 0) break;
+            const double* src = (cell == 0) ? (my + L.in) : (sHaloFlux + nslots);
+            for (int md = lane; md < N; md += LANES) {
+                const int kind = cfg.kind[md], s0 = cfg.slot0[md], np = cfg.nprog[md];
+                const double m0 = src[s0] / cfg.norm[s0];
+                const double m1 = src[s0 + 1] / cfg.norm[s0 + 1];
+                const double m2 = (np > 2) ? src[s0 + 2] / cfg.norm[s0 + 2] : 0.0;
+                ModeParams mp;
+                if (args.params_in) {  // get_coal_ints(pdists, coal_data) on given distributions
+                    mp.n = src[s0]; mp.a = src[s0 + 1]; mp.b = (np > 2) ? src[s0 + 2] : 1.0; mp.invalid = 0;
+                } else {
+                    mp = params_from_moments(kind, m0, m1, m2, kind == CLOUDY_GAMMA ? cfg.k_lo : -INFINITY,
+                                             kind == CLOUDY_GAMMA ? cfg.k_hi : INFINITY);
+                }
+                if (mp.invalid && cell == 0 && args.err_count != nullptr && (p0 + grp) < args.n) atomicAdd(args.err_count, 1ULL);
+                if (cell == 0) {
+                    double* par = my + L.par + md * PAR_STRIDE;
+                    double* mom = my + L.mom + md * M;
+                    par[PAR_N] = mp.n; par[PAR_TH] = mp.a; par[PAR_K] = mp.b;
+                    if (cfg.quad[md]) {
+                        par[PAR_INVTH] = 1.0 / mp.a;
+                        par[PAR_LOGTH] = log(mp.a);
+                        const double gk = (kind == CLOUDY_GAMMA) ? tgamma(mp.b) : 1.0;
+                        par[PAR_GK] = gk;
+                        par[PAR_IGK2] = 1.0 / (gk * gk);
+                    }
+                    // moment matrix row, orders 0..M-1, zero beyond N_mom_max (Coalescence.jl:194)
+                    double mq = mp.n;
+                    for (int q = 0; q < M; ++q) {
+                        double val;
+                        if (kind == CLOUDY_LOGNORMAL) val = mp.n * exp(q * mp.a + (double)(q * q) * mp.b * mp.b / 2);
+                        else val = mq;
+                        mom[q] = (q < cfg.n_mom_max) ? val : 0.0;
+                        if (kind == CLOUDY_GAMMA) mq *= mp.a * (mp.b + q);
+                        else if (kind == CLOUDY_EXPONENTIAL) mq *= mp.a * (q + 1.0);
+                        else mq *= mp.a;
+                    }
+                }
+                if (RAIN) {  // sedimentation flux of this mode — Sedimentation.jl:22-37, rainshaft_helpers.jl:74-77
+                    double* fl = (cell == 0) ? (my + L.flux) : sHaloFlux;
+                    for (int q = 0; q < np; ++q) {
+                        double sum = 0.0;
+                        if (mp.n != 0.0) {
+                            for (int v = 0; v < cfg.n_vel; ++v)
+                                sum += -cfg.velv[v] * moment_real(kind, mp.n, mp.a, mp.b, (double)q + cfg.velb[v]);
+                        } else {
+                            for (int v = 0; v < cfg.n_vel; ++v) sum += -cfg.velv[v] * 0.0;
+                        }
+                        fl[s0 + q] = sum * cfg.norm[s0 + q];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // empty-cell test of the rainshaft RHS (rainshaft_helpers.jl:67-68): all normalised moments < eps
+        bool cell_empty = false;
+        if (RAIN) {
+            cell_empty = true;
+            for (int s = 0; s < nslots; ++s) cell_empty = cell_empty && (my[L.in + s] / cfg.norm[s] < kEps);
+        }
+
+        if (!args.flux_only) {
+            // ---- truncated 2-D integrals of every quadrature mode ----
+            if (MPMAX > 0) {
+                for (int md = 0; md < N - 1; ++md) {
+                    if (!cfg.quad[md]) continue;
+                    const double* par = my + L.par + md * PAR_STRIDE;
+                    const double n_md = par[PAR_N];
+                    const bool skip = (n_md == 0.0) || cell_empty;
+                    double* Fk = my + L.F + md * MAXT;
+                    const int Mp = cfg.Mp[md];
+                    if (__all_sync(0xffffffffu, skip)) {
+                        for (int t = lane; t < Mp * (Mp + 1) / 2; t += LANES) Fk[t] = 0.0;
+                        __syncwarp();
+                        continue;
+                    }
+                    const double th = par[PAR_TH], k = par[PAR_K], inv_th = par[PAR_INVTH], log_th = par[PAR_LOGTH];
+                    const double a_top = k + (double)(Mp - 1);
+                    double* gtab = my + L.tab;
+                    // series degree needed by this group: largest z is below X = x_th/θ and below the series limit
+                    const double X = cfg.thr[md] * inv_th;
+                    double zmax = fmin(X, a_top + (double)kSeriesMargin);
+                    int zi = (zmax >= 0.0) ? (int)fmin(zmax, (double)(kSeriesTabLen - 1)) : 0;
+                    int deg = skip ? 1 : kSeriesDeg[zi];
+                    const int deg_w = __reduce_max_sync(0xffffffffu, deg);
+                    int ai = (int)fmin(fmax(a_top, 0.0), 17.0);
+                    const int cfd_w = __reduce_max_sync(0xffffffffu, (int)kCfDepth[ai]);
+                    // series coefficients c_n = 1/(a)_{n+1}, n = 0..deg_w, chunked over the lanes:
+                    // local product → group scan → one division → downward fill
+                    {
+                        const int C = (deg_w + LANES) / LANES;  // chunk length, covers 0..deg_w
+                        const int n0 = lane * C;
+                        double prod = 1.0;
+                        for (int i = 0; i < C; ++i) prod *= (a_top + (double)(n0 + i));
+                        double incl = prod;
+#pragma unroll
+                        for (int off = 1; off < LANES; off <<= 1) {
+                            double o = __shfl_up_sync(0xffffffffu, incl, off, LANES);
+                            if (lane >= off) incl *= o;
+                        }
+                        double cc = 1.0 / incl;  // c at the top of my chunk: 1/(a)_{n0+C}
+                        for (int i = C - 1; i >= 0; --i) {
+                            const int n = n0 + i;
+                            if (n <= kSeriesMaxDeg) gtab[TAB_CT + n] = cc;
+                            cc *= (a_top + (double)n);
+                        }
+                        for (int i = lane; i < (Mp - 1) + cfd_w; i += LANES) {
+                            if (i < Mp - 1) gtab[TAB_IA + i] = 1.0 / (k + (double)i);
+                            else {
+                                const double fn = (double)(i - (Mp - 1) + 1);
+                                gtab[TAB_CF + (i - (Mp - 1) + 1)] = fn * (fn - a_top);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    double gam_top = par[PAR_GK];
+                    for (int p = 0; p < Mp - 1; ++p) gam_top *= (k + (double)p);  // Γ(k+Mp-1)
+                    double acc[T];
+                    node_integrals<(MPMAX > 0 ? MPMAX : 1), LANES>(acc, sTab + cfg.tab_off[md], cfg.n_bins[md], M, Mp, k, inv_th, log_th,
+                                                                  gam_top, gtab, deg_w, cfd_w, lane);
+                    // F = 0 | min(Mom*Mom, H) — Coalescence.jl:212-227; H = n²θ^{p2}/Γ(k)² * Σ
+                    const double* mom = my + L.mom + md * M;
+                    const double pre0 = n_md * n_md * par[PAR_IGK2];
+                    {
+                        int t = 0;
+#pragma unroll
+                        for (int p1 = 0; p1 < MPMAX; ++p1) {
+                            double pre = pre0;
+                            for (int q = 0; q < p1; ++q) pre *= th;
+#pragma unroll
+                            for (int p2 = p1; p2 < MPMAX; ++p2) {
+                                if (p1 < Mp && p2 < Mp) {
+                                    const double mm = mom[p1] * mom[p2];
+                                    const double H = pre * acc[t];
+                                    const double v = (mm < kEps) ? 0.0 : jl_min(mm, H);
+                                    const int idx = tri_index(p1, p2, Mp);
+                                    if ((idx % LANES) == lane) Fk[idx] = skip ? 0.0 : v;
+                                }
+                                pre *= th;
+                                ++t;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+            // ---- contraction: one output moment per lane — Coalescence.jl:140-149, :260-455 ----
+            for (int o = lane; o < nslots; o += LANES) {
+                const int k = cfg.slot_mode[o], m = cfg.slot_order[o];
+                double result = 0.0;
+                if (!(RAIN && cell_empty)) {
+                    const double* momk = my + L.mom + k * M;
+                    double bin[3];
+                    bin[0] = 1.0; bin[1] = (m == 2) ? 2.0 : 1.0; bin[2] = 1.0;  // C(m, c)
+                    double sumQ = 0.0, sumR = 0.0;
+                    for (int j = 0; j < N; ++j) {
+                        const double* momj = my + L.mom + j * M;
+                        const double* cjk = sC + ((j * N + k) * P) * P;
+                        if (k > j) {  // Q_jk — :283-309
+                            double q = 0.0;
+                            for (int a = 0; a < P; ++a) {
+                                double qa = 0.0;
+                                for (int b = 0; b < P; ++b) {
+                                    double qb = 0.0;
+                                    for (int c = 0; c <= m; ++c) qb += cjk[a * P + b] * bin[c] * momj[a + c] * momk[b + m - c];
+                                    qa += qb;
+                                }
+                                q += qa;
+                            }
+                            sumQ += q;
+                        }
+                        {  // R_jk — :334-351
+                            double r = 0.0;
+                            for (int a = 0; a < P; ++a) {
+                                double ra = 0.0;
+                                for (int b = 0; b < P; ++b) ra += cjk[a * P + b] * momj[a] * momk[b + m];
+                                r += ra;
+                            }
+                            sumR += r;
+                        }
+                    }
+                    // S_1k — :398-424
+                    double s1 = 0.0;
+                    {
+                        const double* ckk = sC + ((k * N + k) * P) * P;
+                        const double* park = my + L.par + k * PAR_STRIDE;
+                        const double* Fk = my + L.F + (k < N - 1 ? k : 0) * MAXT;
+                        for (int a = 0; a < P; ++a) {
+                            double sa = 0.0;
+                            for (int b = 0; b < P; ++b) {
+                                double sb = 0.0;
+                                for (int c = 0; c <= m; ++c)
+                                    sb += 0.5 * ckk[a * P + b] * bin[c] * F_entry(cfg, momk, park, Fk, k, a + c, b + m - c);
+                                sa += sb;
+                            }
+                            s1 += sa;
+                        }
+                    }
+                    // S_2,k-1 — :426-455 (zero when both modes carry too few moments, :366-369)
+                    double s2 = 0.0;
+                    if (k > 0) {
+                        const int kk = k - 1;
+                        const double* momp = my + L.mom + kk * M;
+                        const double* cpp = sC + ((kk * N + kk) * P) * P;
+                        const double* parp = my + L.par + kk * PAR_STRIDE;
+                        const double* Fp = my + L.F + kk * MAXT;
+                        for (int a = 0; a < P; ++a) {
+                            double sa = 0.0;
+                            for (int b = 0; b < P; ++b) {
+                                double sb = 0.0;
+                                for (int c = 0; c <= m; ++c)
+                                    sb += 0.5 * cpp[a * P + b] * bin[c] *
+                                          (momp[a + c] * momp[b + m - c] - F_entry(cfg, momp, parp, Fp, kk, a + c, b + m - c));
+                                sa += sb;
+                            }
+                            s2 += sa;
+                        }
+                    }
+                    result = sumQ - sumR + s1;
+                    if (k > 0) result += s2;
+                    if (!args.params_in) result *= cfg.norm[o];
+                }
+                my[L.out + o] = result;
+            }
+        }
+        __syncthreads();
+        // ---- store phase ----
+        for (int i = tid; i < nslots * G; i += THREADS) {
+            const int s = i / G, g = i % G;
+            const long long p = p0 + g;
+            if (p >= args.n) continue;
+            const double* rec = sGroups + (size_t)g * L.total;
+            double f;
+            if (RAIN) {
+                const double fl = rec[L.flux + s];
+                if (args.flux_only) {
+                    f = fl;
+                } else {
+                    double fl_up;  // flux of the level above; zero at the column top (rainshaft_helpers.jl:80-81)
+                    if ((p + 1) % cfg.nz == 0) fl_up = 0.0;
+                    else if (g + 1 < G) fl_up = (sGroups + (size_t)(g + 1) * L.total)[L.flux + s];
+                    else fl_up = sHaloFlux[s];
+                    f = rec[L.out + s] + (-(fl_up - fl) / cfg.dz);
+                }
+            } else {
+                f = rec[L.out + s];
+            }
+            double o;
+            if (args.tend_only) {
+                o = f;
+            } else {
+                const double ui = rec[L.in + s];
+                double acc2 = args.ci * ui;
+                if (args.u_n != nullptr) acc2 = args.cn * rec[L.un + s] + acc2;
+                o = (acc2 + args.cf * (args.dt * f)) / args.div;
+                if (RAIN) o = (o < 0.0) ? 0.0 : o;  // clipped by the next RHS evaluation (rainshaft_helpers.jl:52)
+            }
+            args.out[s * args.s_out + p] = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+// AoS [n][nslots] (host order) <-> SoA [nslots][stride]
+__global__ void aos_to_soa_kernel(const double* __restrict__ aos, double* __restrict__ soa, long long n, int nslots, long long stride) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long total = n * nslots;
+    for (; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / nslots;
+        const int s = (int)(i % nslots);
+        soa[s * stride + p] = aos[i];
+    }
+}
+__global__ void soa_to_aos_kernel(const double* __restrict__ soa, double* __restrict__ aos, long long n, int nslots, long long stride) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long total = n * nslots;
+    for (; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / nslots;
+        const int s = (int)(i % nslots);
+        aos[i] = soa[s * stride + p];
+    }
+}
+
+// per-slot sums, deterministic two-pass: block partials (fixed grid) then one block finishes
+constexpr int SUM_BLOCKS = 592;  // 148 SMs x 4
+constexpr int SUM_THREADS = 256;
+__global__ void __launch_bounds__(SUM_THREADS) moment_partial_kernel(const double* __restrict__ u, long long n, long long stride, int nslots,
+                                                                   double* __restrict__ partial) {
+    __shared__ double red[SUM_THREADS / 32];
+    for (int s = 0; s < nslots; ++s) {
+        double acc = 0.0;
+        const double* col = u + s * stride;
+        for (long long p = blockIdx.x * (long long)SUM_THREADS + threadIdx.x; p < n; p += (long long)SUM_BLOCKS * SUM_THREADS) acc += col[p];
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < SUM_THREADS / 32; ++w) t += red[w];
+            partial[s * SUM_BLOCKS + blockIdx.x] = t;
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(SUM_THREADS) moment_final_kernel(const double* __restrict__ partial, int nslots, double* __restrict__ out) {
+    __shared__ double red[SUM_THREADS / 32];
+    for (int s = 0; s < nslots; ++s) {
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < SUM_BLOCKS; i += SUM_THREADS) acc += partial[s * SUM_BLOCKS + i];
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < SUM_THREADS / 32; ++w) t += red[w];
+            out[s] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// single-object evaluations (arbitrary real orders): one warp
+struct ScalarArgs {
+    int op;  // 0 moment, 1 update_dist, 2 moment_source_helper, 3 sed flux, 4 simpson
+    int kind;
+    double params[3];
+    double q, p1, p2, x_th;
+    int n_bins;
+    double x_min, dx;
+    double range[4];
+    int n_modes, n_vel;
+    int kinds[MAXN];
+    double mparams[MAXN][3];
+    double vel[CLOUDY_MAX_VEL][2];
+    const double* y;  // simpson table (device)
+    double* out;      // device
+    int* iout;
+};
+
+__device__ inline double simpson_weight(int j, int n_bins) {  // 1-based node j of ParticleDistributions.jl:698-710 (numerators /48)
+    const int e = n_bins + 1;
+    double w = 0.0;
+    if (j >= 5 && j <= n_bins - 3) w += 48.0;
+    if (j == 1 || j == e) w += 17.0;
+    if (j == 2 || j == e - 1) w += 59.0;
+    if (j == 3 || j == e - 2) w += 43.0;
+    if (j == 4 || j == e - 3) w += 49.0;
+    return w;
+}
+
+__global__ void scalar_kernel(const ScalarArgs a) {
+    const int lane = threadIdx.x;
+    if (a.op == 0) {
+        if (lane == 0) a.out[0] = moment_real(a.kind, a.params[0], a.params[1], a.params[2], a.q);
+    } else if (a.op == 1) {
+        if (lane == 0) {
+            ModeParams r = params_from_moments(a.kind, a.params[0], a.params[1], a.params[2], a.range[0], a.range[1], a.range[2], a.range[3]);
+            a.out[0] = r.n; a.out[1] = r.a; a.out[2] = r.b;
+            a.iout[0] = r.invalid;
+        }
+    } else if (a.op == 2) {
+        // moment_source_helper for Exponential / Gamma with real p1, p2 (ParticleDistributions.jl:567-612)
+        const double n = a.params[0], th = a.params[1];
+        const double k = (a.kind == CLOUDY_GAMMA) ? a.params[2] : 1.0;
+        double part = 0.0;
+        for (int j = 1 + lane; j <= a.n_bins; j += 32) {
+            const double x = exp(a.x_min + (j - 1) * a.dx);
+            const double f = pow(x, a.p1 + k - 1.0) * exp(-x / th) * igam_lower(a.p2 + k, (a.x_th - x) / th);
+            part += simpson_weight(j, a.n_bins) * (x * f);
+        }
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+        if (lane == 0) {
+            const double gk = tgamma(k);
+            a.out[0] = n * n * pow(th, a.p2 - k) / (gk * gk) * (a.dx * (part / 48.0));
+        }
+    } else if (a.op == 3) {
+        if (lane == 0) {
+            int o = 0;
+            for (int i = 0; i < a.n_modes; ++i) {
+                const int np = (a.kinds[i] == CLOUDY_GAMMA || a.kinds[i] == CLOUDY_LOGNORMAL) ? 3 : 2;
+                for (int j = 0; j < np; ++j) {
+                    double s = 0.0;
+                    for (int v = 0; v < a.n_vel; ++v)
+                        s += -a.vel[v][0] * moment_real(a.kinds[i], a.mparams[i][0], a.mparams[i][1], a.mparams[i][2], (double)j + a.vel[v][1]);
+                    a.out[o++] = s;
+                }
+            }
+        }
+    } else if (a.op == 4) {
+        double part = 0.0;
+        for (int j = 1 + lane; j <= a.n_bins + 1; j += 32) part += simpson_weight(j, a.n_bins) * a.y[j - 1];
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+        if (lane == 0) a.out[0] = a.dx * (part / 48.0);
+    }
+}
+
+// FP64 peak: independent FMA chains
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+}  // namespace cloudy
+
+// ================================================================================================
+// host side: C ABI
+// ================================================================================================
+using namespace cloudy;
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess) return fail(CLOUDY_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+struct cloudy_state {
+    cloudy_ctx* ctx;
+    double* d;
+    long long n, stride;
+    int nslots;
+};
+
+struct cloudy_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    bool configured;
+    cloudy_config cfg;
+    DevConfig dev;
+    double* d_tab;
+    int lanes;
+    int mpmax;  // kernel instance: 0, 4, 5, 7
+    int64_t launches;
+    int sm_count;
+    unsigned long long* d_err;
+    double* d_partial;
+    double* d_scratch;     // small device scratch for scalar entry points
+    cloudy_state* tmp[3];  // stepper / host-path work buffers
+    double* d_stage_aos;   // staging for upload/download
+    long long stage_cap;
+};
+
+typedef void (*rhs_fn)(const DevConfig, const KArgs);
+struct KernelEntry {
+    rhs_fn fn;
+    int threads, groups;
+};
+
+template <int MPMAX, int LANES, int MODEL>
+static KernelEntry entry() {
+    return KernelEntry{(rhs_fn)rhs_kernel<MPMAX, LANES, MODEL>, Shape<LANES>::kThreads, Shape<LANES>::kGroups};
+}
+template <int LANES, int MODEL>
+static KernelEntry pick_mp(int mpmax) {
+    switch (mpmax) {
+        case 0: return entry<0, LANES, MODEL>();
+        case 4: return entry<4, LANES, MODEL>();
+        case 5: return entry<5, LANES, MODEL>();
+        default: return entry<7, LANES, MODEL>();
+    }
+}
+template <int MODEL>
+static KernelEntry pick_lanes(int lanes, int mpmax) {
+    switch (lanes) {
+        case 4: return pick_mp<4, MODEL>(mpmax);
+        case 16: return pick_mp<16, MODEL>(mpmax);
+        case 32: return pick_mp<32, MODEL>(mpmax);
+        default: return pick_mp<8, MODEL>(mpmax);
+    }
+}
+
+static int launch_rhs(cloudy_ctx* ctx, int model, const KArgs& args) {
+    KernelEntry ke = (model == CLOUDY_MODEL_RAINSHAFT) ? pick_lanes<MODEL_RAINSHAFT>(ctx->lanes, ctx->mpmax)
+                                                       : pick_lanes<MODEL_BOX>(ctx->lanes, ctx->mpmax);
+    const DevConfig& d = ctx->dev;
+    const bool rain = (model == CLOUDY_MODEL_RAINSHAFT);
+    GroupLayout L = group_layout(d.N, d.M, d.nslots, rain);
+    size_t smem = sizeof(double) * ((size_t)d.N * d.N * d.P * d.P + d.tab_total + (size_t)ke.groups * L.total + 2 * d.nslots + 2);
+    if (smem > 227 * 1024) return fail(CLOUDY_ERR_UNSUPPORTED, "configuration needs more than 227 KB of shared memory per block");
+    CUDA_TRY(cudaFuncSetAttribute((const void*)ke.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)ke.fn, ke.threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long n_tiles = (args.n + ke.groups - 1) / ke.groups;
+    long long grid = std::min<long long>(n_tiles, (long long)ctx->sm_count * per_sm);
+    if (grid < 1) grid = 1;
+    void* params[2] = {(void*)&ctx->dev, (void*)&args};
+    CUDA_TRY(cudaLaunchKernel((const void*)ke.fn, dim3((unsigned)grid), dim3(ke.threads), params, smem, ctx->stream));
+    ctx->launches++;
+    return CLOUDY_OK;
+}
+
+extern "C" {
+
+const char* cloudy_last_error(void) { return g_last_error.c_str(); }
+
+int cloudy_ctx_create(int device, void* stream, cloudy_ctx** out) {
+    if (!out) return fail(CLOUDY_ERR_ARG, "out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(CLOUDY_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)");
+    if (device < 0 || device >= count) return fail(CLOUDY_ERR_ARG, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    cloudy_ctx* c = new cloudy_ctx();
+    memset((void*)c, 0, sizeof(*c));
+    c->device = device;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+        c->own_stream = false;
+    } else {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    c->lanes = 8;
+    CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaMalloc(&c->d_err, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(c->d_err, 0, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&c->d_partial, sizeof(double) * SUM_BLOCKS * MAXSLOT));
+    CUDA_TRY(cudaMalloc(&c->d_scratch, sizeof(double) * (CLOUDY_MAX_NODES + 64)));
+    *out = c;
+    return CLOUDY_OK;
+}
+
+int cloudy_ctx_destroy(cloudy_ctx* ctx) {
+    if (!ctx) return CLOUDY_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 3; ++i)
+        if (ctx->tmp[i]) cloudy_state_destroy(ctx->tmp[i]);
+    cudaFree(ctx->d_tab);
+    cudaFree(ctx->d_err);
+    cudaFree(ctx->d_partial);
+    cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_stage_aos);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return CLOUDY_OK;
+}
+
+int cloudy_set_lanes(cloudy_ctx* ctx, int lanes) {
+    if (!ctx) return fail(CLOUDY_ERR_ARG, "ctx is NULL");
+    if (lanes == 0) lanes = 8;
+    if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return fail(CLOUDY_ERR_ARG, "lanes must be 4, 8, 16 or 32");
+    ctx->lanes = lanes;
+    return CLOUDY_OK;
+}
+
+int cloudy_launch_count(cloudy_ctx* ctx, int64_t* out) {
+    if (!ctx || !out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    *out = ctx->launches;
+    return CLOUDY_OK;
+}
+
+int cloudy_sync(cloudy_ctx* ctx) {
+    if (!ctx) return fail(CLOUDY_ERR_ARG, "ctx is NULL");
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return CLOUDY_OK;
+}
+
+int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
+    if (!ctx || !cfg) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int N = cfg->n_modes, P = cfg->P;
+    if (N < 1 || N > MAXN) return fail(CLOUDY_ERR_ARG, "n_modes must be 1..4");
+    if (P < 1 || P > MAXP) return fail(CLOUDY_ERR_ARG, "P must be 1..5");
+    if (!(cfg->norms[0] > 0) || !(cfg->norms[1] > 0)) return fail(CLOUDY_ERR_ARG, "norms must be positive!");
+    if (cfg->threshold_style != CLOUDY_FIXED_THRESHOLD)
+        return fail(CLOUDY_ERR_UNSUPPORTED, "MovingThreshold is not implemented yet (SURVEY §8(f) rank 1)");
+    DevConfig d;
+    memset((void*)&d, 0, sizeof(d));
+    d.N = N; d.P = P; d.M = P + 2;
+    int slot = 0;
+    for (int i = 0; i < N; ++i) {
+        const int kind = cfg->kind[i];
+        if (kind < 0 || kind > 3) return fail(CLOUDY_ERR_ARG, "unknown distribution kind");
+        const int np = (kind == CLOUDY_GAMMA || kind == CLOUDY_LOGNORMAL) ? 3 : 2;
+        if (cfg->nprog[i] != np) return fail(CLOUDY_ERR_ARG, "nprog[i] must equal nparams of the distribution kind");
+        d.kind[i] = kind; d.nprog[i] = np; d.slot0[i] = slot;
+        for (int q = 0; q < np; ++q) {
+            d.slot_mode[slot] = i; d.slot_order[slot] = q;
+            d.norm[slot] = cfg->norms[0] * pow(cfg->norms[1], (double)q);  // helper_functions.jl:49
+            ++slot;
+        }
+    }
+    d.nslots = slot;
+    d.thr_style = cfg->threshold_style;
+    d.n_mom_max = cfg->n_mom_max;
+    d.k_lo = cfg->k_range[0]; d.k_hi = cfg->k_range[1];
+    for (int j = 0; j < N; ++j)
+        for (int k = 0; k < N; ++k)
+            for (int a = 0; a < P; ++a)
+                for (int b = 0; b < P; ++b) {
+                    if (cfg->c[j][k][a][b] != cfg->c[j][k][b][a]) return fail(CLOUDY_ERR_ARG, "array not symmetric.");
+                    d.c[j][k][a][b] = cfg->c[j][k][a][b];
+                }
+    // grid tables
+    std::vector<double> tab;
+    int mpmax = 0;
+    for (int i = 0; i < N; ++i) {
+        d.n2d[i] = cfg->n_2d_ints[i];
+        d.Mp[i] = std::min(d.M, d.n2d[i]);
+        d.thr[i] = cfg->thresholds[i];
+        const bool finite_thr = (i < N - 1) && !std::isinf(cfg->thresholds[i]);
+        if (finite_thr && cfg->kind[i] == CLOUDY_LOGNORMAL)
+            return fail(CLOUDY_ERR_UNSUPPORTED, "Lognormal mode with a finite threshold is not implemented yet");
+        d.mono_thr[i] = finite_thr && cfg->kind[i] == CLOUDY_MONODISPERSE;
+        d.quad[i] = finite_thr && (cfg->kind[i] == CLOUDY_GAMMA || cfg->kind[i] == CLOUDY_EXPONENTIAL);
+        if (d.quad[i]) {
+            const int nb = cfg->n_bins[i];
+            if (!(cfg->thresholds[i] > 0)) return fail(CLOUDY_ERR_ARG, "thresholds must be positive");
+            if (nb < 3) return fail(CLOUDY_ERR_ARG, "n_bins must be at least 3");
+            if (nb > CLOUDY_MAX_NODES) return fail(CLOUDY_ERR_UNSUPPORTED, "n_bins exceeds CLOUDY_MAX_NODES");
+            if (d.Mp[i] < 2) return fail(CLOUDY_ERR_ARG, "N_2d_ints too small");
+            d.n_bins[i] = nb;
+            d.tab_off[i] = (int)tab.size();
+            const double T = cfg->thresholds[i];
+            std::vector<double> xj(nb), ell(nb), tmx(nb), lz(nb), w(nb, 0.0);
+            const int e = nb + 1;
+            auto addw = [&](int j, double v) { if (j >= 1 && j <= nb) w[j - 1] += v; };
+            for (int j = 5; j <= nb - 3; ++j) addw(j, 1.0);
+            addw(1, 17.0 / 48); addw(e, 17.0 / 48);
+            addw(2, 59.0 / 48); addw(e - 1, 59.0 / 48);
+            addw(3, 43.0 / 48); addw(e - 2, 43.0 / 48);
+            addw(4, 49.0 / 48); addw(e - 3, 49.0 / 48);
+            for (int j = 1; j <= nb; ++j) {
+                ell[j - 1] = cfg->x_min[i] + (j - 1) * cfg->dx[i];  // logx, ParticleDistributions.jl:566
+                xj[j - 1] = exp(ell[j - 1]);
+                tmx[j - 1] = T - xj[j - 1];
+                if (!(tmx[j - 1] > 0)) return fail(CLOUDY_ERR_ARG, "grid node at or beyond the threshold");
+                lz[j - 1] = log(tmx[j - 1]);
+            }
+            tab.insert(tab.end(), xj.begin(), xj.end());
+            tab.insert(tab.end(), ell.begin(), ell.end());
+            tab.insert(tab.end(), tmx.begin(), tmx.end());
+            tab.insert(tab.end(), lz.begin(), lz.end());
+            for (int p = 0; p < d.M; ++p)
+                for (int j = 0; j < nb; ++j) tab.push_back(w[j] * cfg->dx[i] * pow(xj[j], (double)p));
+            mpmax = std::max(mpmax, d.Mp[i]);
+        }
+    }
+    d.tab_total = (int)tab.size();
+    cudaFree(ctx->d_tab);
+    ctx->d_tab = nullptr;
+    if (!tab.empty()) {
+        CUDA_TRY(cudaMalloc(&ctx->d_tab, sizeof(double) * tab.size()));
+        CUDA_TRY(cudaMemcpy(ctx->d_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+    }
+    d.tab = ctx->d_tab;
+    d.n_vel = cfg->n_vel;
+    if (d.n_vel < 0 || d.n_vel > CLOUDY_MAX_VEL) return fail(CLOUDY_ERR_ARG, "n_vel out of range");
+    for (int v = 0; v < d.n_vel; ++v) {
+        d.velv[v] = cfg->vel[v][0] * pow(cfg->norms[1], cfg->vel[v][1]);  // rainshaft_helpers.jl:75
+        d.velb[v] = cfg->vel[v][1];
+    }
+    d.nz = cfg->nz > 0 ? cfg->nz : 1;
+    d.dz = cfg->dz;
+    ctx->mpmax = (mpmax == 0) ? 0 : (mpmax <= 4 ? 4 : (mpmax == 5 ? 5 : 7));
+    ctx->dev = d;
+    ctx->cfg = *cfg;
+    ctx->configured = true;
+    for (int i = 0; i < 3; ++i)
+        if (ctx->tmp[i]) { cloudy_state_destroy(ctx->tmp[i]); ctx->tmp[i] = nullptr; }
+    return CLOUDY_OK;
+}
+
+// ---- state ------------------------------------------------------------------------------------
+int cloudy_state_create(cloudy_ctx* ctx, int64_t n_parcels, cloudy_state** out) {
+    if (!ctx || !out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (!ctx->configured) return fail(CLOUDY_ERR_STATE, "cloudy_config_set has not been called");
+    if (n_parcels < 0) return fail(CLOUDY_ERR_ARG, "negative parcel count");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cloudy_state* s = new cloudy_state();
+    s->ctx = ctx;
+    s->n = n_parcels;
+    s->nslots = ctx->dev.nslots;
+    s->stride = ((n_parcels + 31) / 32) * 32;  // 256-byte aligned slot columns
+    if (s->stride == 0) s->stride = 32;
+    s->d = nullptr;
+    cudaError_t e = cudaMalloc(&s->d, sizeof(double) * s->stride * s->nslots);
+    if (e != cudaSuccess) {
+        delete s;
+        return fail(CLOUDY_ERR_CUDA, std::string("cudaMalloc(state): ") + cudaGetErrorString(e));
+    }
+    CUDA_TRY(cudaMemsetAsync(s->d, 0, sizeof(double) * s->stride * s->nslots, ctx->stream));
+    *out = s;
+    return CLOUDY_OK;
+}
+
+int cloudy_state_destroy(cloudy_state* st) {
+    if (!st) return CLOUDY_OK;
+    cudaSetDevice(st->ctx->device);
+    cudaStreamSynchronize(st->ctx->stream);
+    cudaFree(st->d);
+    delete st;
+    return CLOUDY_OK;
+}
+
+int cloudy_state_device_ptr(const cloudy_state* st, double** dptr, int64_t* stride, int32_t* n_slots) {
+    if (!st) return fail(CLOUDY_ERR_ARG, "state is NULL");
+    if (dptr) *dptr = st->d;
+    if (stride) *stride = st->stride;
+    if (n_slots) *n_slots = st->nslots;
+    return CLOUDY_OK;
+}
+
+static int ensure_stage(cloudy_ctx* ctx, long long n_doubles) {
+    if (ctx->stage_cap >= n_doubles) return CLOUDY_OK;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_stage_aos);
+    ctx->d_stage_aos = nullptr;
+    ctx->stage_cap = 0;
+    CUDA_TRY(cudaMalloc(&ctx->d_stage_aos, sizeof(double) * n_doubles));
+    ctx->stage_cap = n_doubles;
+    return CLOUDY_OK;
+}
+
+int cloudy_state_upload(cloudy_ctx* ctx, cloudy_state* st, const double* host, int64_t n_parcels) {
+    if (!ctx || !st || (!host && n_parcels > 0)) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (n_parcels != st->n) return fail(CLOUDY_ERR_ARG, "parcel count does not match the state");
+    if (n_parcels == 0) return CLOUDY_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const long long total = (long long)n_parcels * st->nslots;
+    int rc = ensure_stage(ctx, total);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_stage_aos, host, sizeof(double) * total, cudaMemcpyHostToDevice, ctx->stream));
+    int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    aos_to_soa_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_stage_aos, st->d, n_parcels, st->nslots, st->stride);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    return CLOUDY_OK;
+}
+
+int cloudy_state_download(cloudy_ctx* ctx, const cloudy_state* st, double* host, int64_t n_parcels) {
+    if (!ctx || !st || (!host && n_parcels > 0)) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (n_parcels != st->n) return fail(CLOUDY_ERR_ARG, "parcel count does not match the state");
+    if (n_parcels == 0) return CLOUDY_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const long long total = (long long)n_parcels * st->nslots;
+    int rc = ensure_stage(ctx, total);
+    if (rc) return rc;
+    int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    soa_to_aos_kernel<<<blocks, 256, 0, ctx->stream>>>(st->d, ctx->d_stage_aos, n_parcels, st->nslots, st->stride);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    CUDA_TRY(cudaMemcpyAsync(host, ctx->d_stage_aos, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return CLOUDY_OK;
+}
+
+int cloudy_state_copy(cloudy_ctx* ctx, const cloudy_state* src, cloudy_state* dst) {
+    if (!ctx || !src || !dst) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (src->n != dst->n || src->nslots != dst->nslots) return fail(CLOUDY_ERR_ARG, "state shapes differ");
+    CUDA_TRY(cudaMemcpyAsync(dst->d, src->d, sizeof(double) * src->stride * src->nslots, cudaMemcpyDeviceToDevice, ctx->stream));
+    return CLOUDY_OK;
+}
+
+// ---- hot path -----------------------------------------------------------------------------------
+static int check_pair(cloudy_ctx* ctx, const cloudy_state* a, const cloudy_state* b) {
+    if (!ctx || !a || !b) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (!ctx->configured) return fail(CLOUDY_ERR_STATE, "cloudy_config_set has not been called");
+    if (a->n != b->n || a->nslots != ctx->dev.nslots || b->nslots != ctx->dev.nslots) return fail(CLOUDY_ERR_ARG, "state shapes differ");
+    return CLOUDY_OK;
+}
+
+static KArgs base_args(cloudy_ctx* ctx, const cloudy_state* in, cloudy_state* out) {
+    KArgs a;
+    memset(&a, 0, sizeof(a));
+    a.u_in = in->d; a.s_in = in->stride;
+    a.out = out->d; a.s_out = out->stride;
+    a.n = in->n;
+    a.cn = 0; a.ci = 1; a.cf = 1; a.dt = 1; a.div = 1;
+    a.err_count = ctx->d_err;
+    return a;
+}
+
+int cloudy_coal_tendency(cloudy_ctx* ctx, const cloudy_state* m, cloudy_state* dm) {
+    int rc = check_pair(ctx, m, dm);
+    if (rc) return rc;
+    if (m->n == 0) return CLOUDY_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    KArgs a = base_args(ctx, m, dm);
+    a.tend_only = 1;
+    return launch_rhs(ctx, CLOUDY_MODEL_BOX, a);
+}
+
+int cloudy_sedimentation_flux(cloudy_ctx* ctx, const cloudy_state* m, cloudy_state* flux) {
+    int rc = check_pair(ctx, m, flux);
+    if (rc) return rc;
+    if (m->n == 0) return CLOUDY_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    KArgs a = base_args(ctx, m, flux);
+    a.tend_only = 1;
+    a.flux_only = 1;
+    return launch_rhs(ctx, CLOUDY_MODEL_RAINSHAFT, a);
+}
+
+int cloudy_rainshaft_rhs(cloudy_ctx* ctx, cloudy_state* m, cloudy_state* dm) {
+    int rc = check_pair(ctx, m, dm);
+    if (rc) return rc;
+    if (m->n == 0) return CLOUDY_OK;
+    if (m->n % ctx->dev.nz != 0) return fail(CLOUDY_ERR_ARG, "cell count is not a multiple of nz");
+    if (!(ctx->dev.dz > 0)) return fail(CLOUDY_ERR_ARG, "dz must be positive");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    KArgs a = base_args(ctx, m, dm);
+    a.tend_only = 1;
+    a.clip_back = m->d;
+    a.s_clip = m->stride;
+    return launch_rhs(ctx, CLOUDY_MODEL_RAINSHAFT, a);
+}
+
+static int ensure_tmp(cloudy_ctx* ctx, int idx, long long n) {
+    if (ctx->tmp[idx] && ctx->tmp[idx]->n == n) return CLOUDY_OK;
+    if (ctx->tmp[idx]) { cloudy_state_destroy(ctx->tmp[idx]); ctx->tmp[idx] = nullptr; }
+    return cloudy_state_create(ctx, n, &ctx->tmp[idx]);
+}
+
+int cloudy_ssprk33_steps(cloudy_ctx* ctx, cloudy_state* u, double dt, int32_t n_steps, int32_t model) {
+    if (!ctx || !u) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (!ctx->configured) return fail(CLOUDY_ERR_STATE, "cloudy_config_set has not been called");
+    if (model != CLOUDY_MODEL_BOX && model != CLOUDY_MODEL_RAINSHAFT) return fail(CLOUDY_ERR_ARG, "unknown model");
+    if (n_steps < 0) return fail(CLOUDY_ERR_ARG, "negative step count");
+    if (u->n == 0 || n_steps == 0) return CLOUDY_OK;
+    if (model == CLOUDY_MODEL_RAINSHAFT) {
+        if (u->n % ctx->dev.nz != 0) return fail(CLOUDY_ERR_ARG, "cell count is not a multiple of nz");
+        if (!(ctx->dev.dz > 0)) return fail(CLOUDY_ERR_ARG, "dz must be positive");
+    }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_tmp(ctx, 0, u->n))) return rc;
+    if ((rc = ensure_tmp(ctx, 1, u->n))) return rc;
+    if ((rc = ensure_tmp(ctx, 2, u->n))) return rc;
+    // u^n lives in `cur`; stage results ping-pong through the two other buffers; the caller's buffer
+    // receives the final state.
+    double* cur = u->d;
+    double* t1 = ctx->tmp[0]->d;
+    double* t2 = ctx->tmp[1]->d;
+    double* nxt = ctx->tmp[2]->d;
+    const long long st = u->stride;  // all four share the stride (same n)
+    for (int step = 0; step < n_steps; ++step) {
+        KArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n = u->n; a.dt = dt; a.err_count = ctx->d_err;
+        a.s_in = a.s_n = a.s_out = st;
+        // stage 1: tmp = u + dt f(u)
+        a.u_in = cur; a.u_n = nullptr; a.out = t1; a.cn = 0; a.ci = 1; a.cf = 1; a.div = 1;
+        if ((rc = launch_rhs(ctx, model, a))) return rc;
+        // stage 2: tmp = (3u + tmp + dt f(tmp))/4
+        a.u_in = t1; a.u_n = cur; a.out = t2; a.cn = 3; a.ci = 1; a.cf = 1; a.div = 4;
+        if ((rc = launch_rhs(ctx, model, a))) return rc;
+        // stage 3: u = (u + 2 tmp + 2 dt f(tmp))/3
+        a.u_in = t2; a.u_n = cur; a.out = nxt; a.cn = 1; a.ci = 2; a.cf = 2; a.div = 3;
+        if ((rc = launch_rhs(ctx, model, a))) return rc;
+        std::swap(cur, nxt);
+    }
+    if (cur != u->d) {
+        // odd number of swaps: `cur` is a work buffer; hand its storage to the caller's state
+        std::swap(u->d, ctx->tmp[2]->d);
+    }
+    return CLOUDY_OK;
+}
+
+int cloudy_moment_sums_device(cloudy_ctx* ctx, const cloudy_state* u, double* d_out) {
+    if (!ctx || !u || !d_out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    moment_partial_kernel<<<SUM_BLOCKS, SUM_THREADS, 0, ctx->stream>>>(u->d, u->n, u->stride, u->nslots, ctx->d_partial);
+    CUDA_TRY(cudaGetLastError());
+    moment_final_kernel<<<1, SUM_THREADS, 0, ctx->stream>>>(ctx->d_partial, u->nslots, d_out);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches += 2;
+    return CLOUDY_OK;
+}
+
+int cloudy_moment_sums(cloudy_ctx* ctx, const cloudy_state* u, double* host_out) {
+    if (!ctx || !u || !host_out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    int rc = cloudy_moment_sums_device(ctx, u, ctx->d_scratch);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(host_out, ctx->d_scratch, sizeof(double) * u->nslots, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return CLOUDY_OK;
+}
+
+int cloudy_coal_tendency_host(cloudy_ctx* ctx, const double* host_m, double* host_dm, int64_t n_parcels) {
+    if (!ctx || (!host_m && n_parcels) || (!host_dm && n_parcels)) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (!ctx->configured) return fail(CLOUDY_ERR_STATE, "cloudy_config_set has not been called");
+    if (n_parcels == 0) return CLOUDY_OK;
+    int rc;
+    if ((rc = ensure_tmp(ctx, 0, n_parcels))) return rc;
+    if ((rc = ensure_tmp(ctx, 1, n_parcels))) return rc;
+    if ((rc = cloudy_state_upload(ctx, ctx->tmp[0], host_m, n_parcels))) return rc;
+    if ((rc = cloudy_coal_tendency(ctx, ctx->tmp[0], ctx->tmp[1]))) return rc;
+    return cloudy_state_download(ctx, ctx->tmp[1], host_dm, n_parcels);
+}
+
+int cloudy_error_count(cloudy_ctx* ctx, int64_t* n_invalid) {
+    if (!ctx || !n_invalid) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    unsigned long long v = 0;
+    CUDA_TRY(cudaMemcpyAsync(&v, ctx->d_err, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_err, 0, sizeof(v), ctx->stream));
+    *n_invalid = (int64_t)v;
+    return CLOUDY_OK;
+}
+
+// ---- single-object entry points -------------------------------------------------------------------
+static int run_scalar(cloudy_ctx* ctx, ScalarArgs& a, double* host_out, int n_out, int32_t* host_iout) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    a.out = ctx->d_scratch;
+    a.iout = (int*)(ctx->d_scratch + 32);
+    scalar_kernel<<<1, 32, 0, ctx->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    CUDA_TRY(cudaMemcpyAsync(host_out, a.out, sizeof(double) * n_out, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_iout) CUDA_TRY(cudaMemcpyAsync(host_iout, a.iout, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return CLOUDY_OK;
+}
+
+static int kind_nparams(int kind) { return (kind == CLOUDY_GAMMA || kind == CLOUDY_LOGNORMAL) ? 3 : 2; }
+
+int cloudy_moment(cloudy_ctx* ctx, int32_t kind, const double* params, double q, double* out) {
+    if (!ctx || !params || !out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (kind < 0 || kind > 3) return fail(CLOUDY_ERR_ARG, "unknown distribution kind");
+    ScalarArgs a;
+    memset(&a, 0, sizeof(a));
+    a.op = 0; a.kind = kind; a.q = q;
+    a.params[2] = 1.0;
+    for (int i = 0; i < kind_nparams(kind); ++i) a.params[i] = params[i];
+    return run_scalar(ctx, a, out, 1, nullptr);
+}
+
+int cloudy_update_dist_from_moments(cloudy_ctx* ctx, int32_t kind, const double* moments, const double* range, double* params_out,
+                                    int32_t* invalid) {
+    if (!ctx || !moments || !params_out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (kind < 0 || kind > 3) return fail(CLOUDY_ERR_ARG, "unknown distribution kind");
+    ScalarArgs a;
+    memset(&a, 0, sizeof(a));
+    a.op = 1; a.kind = kind;
+    for (int i = 0; i < kind_nparams(kind); ++i) a.params[i] = moments[i];
+    if (kind == CLOUDY_GAMMA) {
+        a.range[0] = range ? range[0] : kEps;
+        a.range[1] = range ? range[1] : 10.0;
+    } else if (kind == CLOUDY_LOGNORMAL) {
+        a.range[0] = range ? range[0] : -INFINITY;
+        a.range[1] = range ? range[1] : INFINITY;
+        a.range[2] = range ? range[2] : kEps;
+        a.range[3] = range ? range[3] : INFINITY;
+    }
+    double o[3];
+    int32_t inv = 0;
+    int rc = run_scalar(ctx, a, o, 3, &inv);
+    if (rc) return rc;
+    for (int i = 0; i < kind_nparams(kind); ++i) params_out[i] = o[i];
+    if (invalid) *invalid = inv;
+    return CLOUDY_OK;
+}
+
+int cloudy_moment_source_helper(cloudy_ctx* ctx, int32_t kind, const double* params, double p1, double p2, double x_threshold,
+                                int32_t n_bins_per_log_unit, double* out) {
+    if (!ctx || !params || !out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (kind == CLOUDY_MONODISPERSE) {  // closed form, still evaluated on the device through moment()
+        ScalarArgs a;
+        memset(&a, 0, sizeof(a));
+        a.op = 0; a.kind = CLOUDY_MONODISPERSE; a.q = p1 + p2;
+        a.params[0] = params[0] * params[0]; a.params[1] = params[1]; a.params[2] = 1.0;
+        double v;
+        int rc = run_scalar(ctx, a, &v, 1, nullptr);
+        if (rc) return rc;
+        *out = (params[1] < x_threshold / 2) ? v : 0.0;
+        return CLOUDY_OK;
+    }
+    if (kind != CLOUDY_EXPONENTIAL && kind != CLOUDY_GAMMA)
+        return fail(CLOUDY_ERR_UNSUPPORTED, "moment_source_helper: Lognormal is not implemented yet");
+    if (!(x_threshold > 0)) return fail(CLOUDY_ERR_ARG, "x_threshold must be positive");
+    ScalarArgs a;
+    memset(&a, 0, sizeof(a));
+    a.op = 2; a.kind = kind; a.p1 = p1; a.p2 = p2; a.x_th = x_threshold;
+    a.params[2] = 1.0;
+    for (int i = 0; i < kind_nparams(kind); ++i) a.params[i] = params[i];
+    // node grid, ParticleDistributions.jl:579-582
+    const double x_lb = std::min(1e-5, 1e-5 * x_threshold);
+    a.n_bins = (int)floor(n_bins_per_log_unit * log10(x_threshold / x_lb));
+    if (a.n_bins < 3) return fail(CLOUDY_ERR_ARG, "n_bins must be at least 3");
+    a.x_min = log(x_lb);
+    a.dx = (log(x_threshold) - log(x_lb)) / a.n_bins;
+    return run_scalar(ctx, a, out, 1, nullptr);
+}
+
+int cloudy_get_sedimentation_flux_1(cloudy_ctx* ctx, int32_t n_modes, const int32_t* kinds, const double* params, int32_t n_vel,
+                                    const double* vel, double* out) {
+    if (!ctx || !kinds || !params || !vel || !out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (n_modes < 1 || n_modes > MAXN || n_vel < 0 || n_vel > CLOUDY_MAX_VEL) return fail(CLOUDY_ERR_ARG, "size out of range");
+    ScalarArgs a;
+    memset(&a, 0, sizeof(a));
+    a.op = 3; a.n_modes = n_modes; a.n_vel = n_vel;
+    int nout = 0;
+    for (int i = 0; i < n_modes; ++i) {
+        a.kinds[i] = kinds[i];
+        for (int j = 0; j < 3; ++j) a.mparams[i][j] = params[i * 3 + j];
+        nout += kind_nparams(kinds[i]);
+    }
+    for (int v = 0; v < n_vel; ++v) { a.vel[v][0] = vel[2 * v]; a.vel[v][1] = vel[2 * v + 1]; }
+    return run_scalar(ctx, a, out, nout, nullptr);
+}
+
+int cloudy_integrate_simpson(cloudy_ctx* ctx, int32_t n_bins, double dx, const double* y, double* out) {
+    if (!ctx || !y || !out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (n_bins < 3) return fail(CLOUDY_ERR_ARG, "n_bins must be at least 3");
+    if (n_bins + 1 > CLOUDY_MAX_NODES) return fail(CLOUDY_ERR_UNSUPPORTED, "too many nodes");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_scratch + 64, y, sizeof(double) * (n_bins + 1), cudaMemcpyHostToDevice, ctx->stream));
+    ScalarArgs a;
+    memset(&a, 0, sizeof(a));
+    a.op = 4; a.n_bins = n_bins; a.dx = dx; a.y = ctx->d_scratch + 64;
+    return run_scalar(ctx, a, out, 1, nullptr);
+}
+
+int cloudy_get_coal_ints_1(cloudy_ctx* ctx, const double* params, double* out) {
+    if (!ctx || !params || !out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (!ctx->configured) return fail(CLOUDY_ERR_STATE, "cloudy_config_set has not been called");
+    // one parcel whose "state" holds the distribution parameters themselves (params_in): the kernel skips
+    // update_dist_from_moments and the de-normalisation, so the output is the reference's return value.
+    const DevConfig& d = ctx->dev;
+    int rc;
+    if ((rc = ensure_tmp(ctx, 0, 1))) return rc;
+    if ((rc = ensure_tmp(ctx, 1, 1))) return rc;
+    double h[MAXSLOT];
+    for (int i = 0; i < d.N; ++i)
+        for (int q = 0; q < d.nprog[i]; ++q) h[d.slot0[i] + q] = params[3 * i + q];
+    if ((rc = cloudy_state_upload(ctx, ctx->tmp[0], h, 1))) return rc;
+    KArgs a = base_args(ctx, ctx->tmp[0], ctx->tmp[1]);
+    a.tend_only = 1;
+    a.params_in = 1;
+    if ((rc = launch_rhs(ctx, CLOUDY_MODEL_BOX, a))) return rc;
+    return cloudy_state_download(ctx, ctx->tmp[1], out, 1);
+}
+
+int cloudy_measure_fp64_peak(cloudy_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 15;
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, 1024, 0.999999, 1e-7);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+        dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters, 0.999999, 1e-7);
+        CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+        best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    ctx->launches += 6;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return CLOUDY_OK;
+}
+
+}  // extern "C"

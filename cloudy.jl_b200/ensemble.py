@@ -1,0 +1,169 @@
+"""Batched device state and the ODE right-hand sides that consume the hot path.
+
+``ParcelEnsemble`` holds the prognostic moments of many independent parcels (box model) or of the cells of
+many columns (rainshaft) on the GPU, structure-of-arrays.  ``make_box_model_rhs`` / ``make_rainshaft_rhs``
+mirror test/examples/utils/box_model_helpers.jl:22-53 and rainshaft_helpers.jl:45-88 for one parcel /
+column (the reference's calling convention) and for ensembles."""
+import ctypes as C
+from types import SimpleNamespace
+
+import numpy as np
+
+from . import _lib as L
+from .coalescence import (AnalyticalCoalStyle, CoalescenceData, FixedThreshold, MovingThreshold, apply_config,
+                          build_config)
+from .context import Context, default_context
+from .distributions import nparams
+
+
+class ModelParameters(SimpleNamespace):
+    """The drivers' ``ODE_parameters`` named tuple: pdists, coal_data, NProgMoms, norms, dt[, vel, dz]
+    (box_gamma_mixture.jl:30-36, rainshaft_gamma_mixture.jl:39-47)."""
+
+
+class ParcelEnsemble:
+    """Device-resident moments of ``n`` parcels / cells; slot order = the reference's flat moment vector."""
+
+    def __init__(self, ctx: Context, n: int):
+        self.ctx = ctx
+        self.n = int(n)
+        h = C.c_void_p()
+        L.check(L.load().cloudy_state_create(ctx.handle, self.n, C.byref(h)))
+        self.handle = h
+        ns = C.c_int32()
+        st = C.c_int64()
+        p = C.c_void_p()
+        L.check(L.load().cloudy_state_device_ptr(self.handle, C.byref(p), C.byref(st), C.byref(ns)))
+        self.n_slots, self.stride = ns.value, st.value
+
+    def device_ptr(self):
+        p = C.c_void_p()
+        L.check(L.load().cloudy_state_device_ptr(self.handle, C.byref(p), None, None))
+        return p.value
+
+    def upload(self, host):
+        a = np.ascontiguousarray(host, dtype=np.float64)
+        if a.shape != (self.n, self.n_slots):
+            raise ValueError(f"expected host array of shape {(self.n, self.n_slots)}, got {a.shape}")
+        L.check(L.load().cloudy_state_upload(self.ctx.handle, self.handle, L.dptr(a), self.n))
+        self.ctx.sync()  # the staging buffer is reused; keep `a` alive until the copy has landed
+        return self
+
+    def download(self, out=None):
+        a = out if out is not None else np.empty((self.n, self.n_slots), dtype=np.float64)
+        L.check(L.load().cloudy_state_download(self.ctx.handle, self.handle, L.dptr(a), self.n))
+        return a
+
+    def close(self):
+        if getattr(self, "handle", None):
+            L.load().cloudy_state_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CoalescenceModel:
+    """Run-constant configuration on a device context + the batched operators."""
+
+    def __init__(self, par, ctx: Context = None, nz: int = 1):
+        self.ctx = ctx or default_context()
+        self.par = par
+        self.kinds = tuple(d.kind for d in par.pdists)
+        self.NProgMoms = tuple(par.NProgMoms)
+        if tuple(nparams(d) for d in par.pdists) != self.NProgMoms:
+            raise ValueError("NProgMoms does not match the distributions")
+        self.nz = int(nz)
+        self.cfg = build_config(self.kinds, par.coal_data, norms=par.norms, vel=getattr(par, "vel", ()),
+                                dz=getattr(par, "dz", 1.0), nz=self.nz)
+        self._key = ("model", id(self))
+        self.n_slots = sum(self.NProgMoms)
+        self.activate()
+
+    def activate(self):
+        apply_config(self.ctx, self.cfg, key=self._key)
+
+    def ensemble(self, n: int) -> ParcelEnsemble:
+        self.activate()
+        return ParcelEnsemble(self.ctx, n)
+
+    # ---- batched operators -----------------------------------------------------------------------
+    def coal_tendency(self, m: ParcelEnsemble, dm: ParcelEnsemble):
+        self.activate()
+        L.check(L.load().cloudy_coal_tendency(self.ctx.handle, m.handle, dm.handle))
+
+    def sedimentation_flux(self, m: ParcelEnsemble, flux: ParcelEnsemble):
+        self.activate()
+        L.check(L.load().cloudy_sedimentation_flux(self.ctx.handle, m.handle, flux.handle))
+
+    def rainshaft_rhs(self, m: ParcelEnsemble, dm: ParcelEnsemble):
+        self.activate()
+        L.check(L.load().cloudy_rainshaft_rhs(self.ctx.handle, m.handle, dm.handle))
+
+    def ssprk33_steps(self, u: ParcelEnsemble, dt: float, n_steps: int, model: int = L.MODEL_BOX):
+        self.activate()
+        L.check(L.load().cloudy_ssprk33_steps(self.ctx.handle, u.handle, float(dt), int(n_steps), int(model)))
+
+    def moment_sums(self, u: ParcelEnsemble):
+        out = np.zeros(self.n_slots)
+        L.check(L.load().cloudy_moment_sums(self.ctx.handle, u.handle, L.dptr(out)))
+        return out
+
+    def moment_sums_device(self, u: ParcelEnsemble, d_out_ptr: int):
+        L.check(L.load().cloudy_moment_sums_device(self.ctx.handle, u.handle, C.c_void_p(d_out_ptr)))
+
+    def coal_tendency_host(self, host_m, host_dm=None):
+        a = np.ascontiguousarray(host_m, dtype=np.float64)
+        out = host_dm if host_dm is not None else np.empty_like(a)
+        self.activate()
+        L.check(L.load().cloudy_coal_tendency_host(self.ctx.handle, L.dptr(a), L.dptr(out), a.shape[0]))
+        return out
+
+
+def make_box_model_rhs(coal_type, threshold_style=None):
+    """make_box_model_rhs(coal_type, threshold_style) — box_model_helpers.jl:22-27.  Returns ``rhs!(dm, m, par, t)``;
+    ``m``/``dm`` are one moment vector (the reference's call) or an (n_parcels, n_moments) array."""
+    if not isinstance(coal_type, AnalyticalCoalStyle):
+        raise ValueError("Invalid coal style!")
+    threshold_style = threshold_style or FixedThreshold()
+    cache = {}
+
+    def rhs(dm, m, par, t):
+        if isinstance(threshold_style, MovingThreshold) != isinstance(par.coal_data.threshold_style, MovingThreshold):
+            raise ValueError("threshold style does not match coal_data")
+        model = cache.get(id(par))
+        if model is None:
+            model = cache[id(par)] = CoalescenceModel(par)
+        a = np.atleast_2d(np.asarray(m, dtype=np.float64))
+        out = model.coal_tendency_host(a)
+        np.asarray(dm)[...] = out.reshape(np.shape(dm))
+        return dm
+
+    return rhs
+
+
+def make_rainshaft_rhs(coal_type):
+    """make_rainshaft_rhs(coal_type) — rainshaft_helpers.jl:45-88.  Returns ``rhs(m, p, t)`` for an (nz, nmom)
+    column (or (ncol, nz, nmom) columns); ``m`` is clipped at zero IN PLACE like the reference (:52)."""
+    if not isinstance(coal_type, AnalyticalCoalStyle):
+        raise ValueError("Invalid coal style!")
+    cache = {}
+
+    def rhs(m, p, t):
+        m = np.asarray(m)
+        nz = m.shape[-2]
+        key = (id(p), nz)
+        model = cache.get(key)
+        if model is None:
+            model = cache[key] = CoalescenceModel(p, nz=nz)
+        flat = np.ascontiguousarray(m.reshape(-1, m.shape[-1]), dtype=np.float64)
+        u = model.ensemble(flat.shape[0]).upload(flat)
+        du = model.ensemble(flat.shape[0])
+        model.rainshaft_rhs(u, du)
+        m[...] = u.download().reshape(m.shape)
+        return du.download().reshape(m.shape)
+
+    return rhs

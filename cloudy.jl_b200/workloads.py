@@ -1,0 +1,155 @@
+"""Synthetic workloads of BASELINE.json's configs: run-constant model parameters plus a seeded
+generator of parcel / cell states.  Pure numpy host code; used by tests and bench.py."""
+import math
+from types import SimpleNamespace
+
+import numpy as np
+
+from . import _lib as L
+from .coalescence import CoalescenceData
+from .distributions import (ExponentialPrimitiveParticleDistribution as Exp, GammaPrimitiveParticleDistribution as Gam,
+                            LognormalPrimitiveParticleDistribution as LogN, MonodispersePrimitiveParticleDistribution as Mono)
+from .ensemble import ModelParameters
+from .kernel_tensors import CoalescenceTensor, HydrodynamicKernelFunction, LongKernelFunction, polyfit
+
+SEED0 = 20250117
+NORMS = (1e6, 1e-9)
+
+
+def _norm_factors(NProgMoms, norms):
+    return np.array([norms[0] * norms[1] ** q for n in NProgMoms for q in range(n)])
+
+
+def _moments_from_params(kind, n, a, b, nprog):
+    """Normalised moments M_0..M_{nprog-1} (vectorised get_moments, ParticleDistributions.jl:293-315)."""
+    if kind == L.GAMMA:
+        cols = [n, n * b * a, n * b * (b + 1) * a ** 2]
+    elif kind == L.LOGNORMAL:
+        cols = [n, n * np.exp(a + b ** 2 / 2), n * np.exp(2.0 * a + 2.0 * b ** 2)]
+    else:
+        cols = [n, n * a]
+    return np.stack(cols[:nprog], axis=1)
+
+
+def _logu(rng, lo, hi, size):
+    return np.exp(rng.uniform(math.log(lo), math.log(hi), size))
+
+
+def linear_tensor(B=5.0):
+    """Exact tensor of LinearKernelFunction(B): K = B (x + y) (box_gamma_mixture.jl:20-21)."""
+    return CoalescenceTensor(np.array([[0.0, B], [B, 0.0]]))
+
+
+def c1_smoluchowski():
+    """C1: single Exponential mode, constant kernel, 1 parcel (test_Sources_correctness.jl:41-64)."""
+    ker = CoalescenceTensor(np.array([[1.0]]))
+    pd = (Exp(1.0, 1.0),)
+    par = ModelParameters(pdists=pd, coal_data=CoalescenceData(ker, (2,), (math.inf,)), NProgMoms=(2,), norms=(1.0, 1.0), dt=1e-4)
+    return par, np.array([[1.0, 2.0]])
+
+
+def c2_gamma_exp(n_parcels=1 << 20, seed=SEED0 + 2, empty_frac=0.02):
+    """C2/C5: Gamma cloud + Exponential rain, Golovin kernel, thresholds (0.5, Inf) normalised."""
+    rng = np.random.default_rng(seed)
+    NProgMoms = (3, 2)
+    pd = (Gam(1e8, 1e-10, 1.0), Exp(1.0, 1e-8))
+    cd = CoalescenceData(linear_tensor(5.0), NProgMoms, (5e-10, math.inf), NORMS)
+    par = ModelParameters(pdists=pd, coal_data=cd, NProgMoms=NProgMoms, norms=NORMS, dt=10.0)
+    n1 = _logu(rng, 1e1, 1e3, n_parcels); th1 = _logu(rng, 0.03, 0.3, n_parcels); k1 = _logu(rng, 0.5, 5.0, n_parcels)
+    n2 = _logu(rng, 1e-6, 1e0, n_parcels); th2 = _logu(rng, 1.0, 30.0, n_parcels)
+    m = np.concatenate([_moments_from_params(L.GAMMA, n1, th1, k1, 3), _moments_from_params(L.EXPONENTIAL, n2, th2, None, 2)], axis=1)
+    empty = rng.random(n_parcels) < empty_frac
+    m[empty, :] = 0.0
+    return par, m * _norm_factors(NProgMoms, NORMS)
+
+
+def c2_gamma_gamma(n_parcels=4096, seed=SEED0 + 22):
+    """The 6-moment Gamma+Gamma variant of box_gamma_mixture.jl:14-28."""
+    rng = np.random.default_rng(seed)
+    NProgMoms = (3, 3)
+    pd = (Gam(1e8, 1e-10, 1.0), Gam(1.0, 1e-8, 1.0))
+    cd = CoalescenceData(linear_tensor(5.0), NProgMoms, (5e-10, math.inf), NORMS)
+    par = ModelParameters(pdists=pd, coal_data=cd, NProgMoms=NProgMoms, norms=NORMS, dt=10.0)
+    n1 = _logu(rng, 1e1, 1e3, n_parcels); th1 = _logu(rng, 0.03, 0.3, n_parcels); k1 = _logu(rng, 0.5, 5.0, n_parcels)
+    n2 = _logu(rng, 1e-6, 1e0, n_parcels); th2 = _logu(rng, 1.0, 30.0, n_parcels); k2 = _logu(rng, 0.5, 5.0, n_parcels)
+    m = np.concatenate([_moments_from_params(L.GAMMA, n1, th1, k1, 3), _moments_from_params(L.GAMMA, n2, th2, k2, 3)], axis=1)
+    m[0] = np.array([1e8, 1e-2, 2e-12, 1, 1e-8, 2e-16]) / _norm_factors(NProgMoms, NORMS)  # the script's own IC
+    return par, m * _norm_factors(NProgMoms, NORMS)
+
+
+def c3_rainshaft(n_columns=4096, nz=256, seed=SEED0 + 3):
+    """C3: rainshaft, 2 Gamma modes, thresholds (0.2, Inf) normalised, vel = 50 x^(1/6) (rainshaft_gamma_mixture.jl:13-49)."""
+    rng = np.random.default_rng(seed)
+    NProgMoms = (3, 3)
+    pd = (Gam(1e7, 1e-10, 1.0), Gam(0.0, 1e-9, 1.0))
+    cd = CoalescenceData(linear_tensor(5.0), NProgMoms, (2e-10, math.inf), NORMS)
+    zmax = 3000.0
+    dz = zmax / nz
+    par = ModelParameters(pdists=pd, coal_data=cd, NProgMoms=NProgMoms, norms=NORMS, vel=((50.0, 1.0 / 6),), dz=dz, dt=1.0)
+    z = np.arange(dz / 2, zmax, dz)[:nz]
+    at = np.where((z >= 0.5 * zmax - dz / 2) & (z < 0.75 * zmax - dz / 2), 1.0, 0.0)  # rainshaft_helpers.jl:21-27
+    amp = np.array([1e7, 1e-3, 2e-13, 0.0, 0.0, 0.0])
+    fac = _logu(rng, 0.3, 3.0, n_columns)
+    m = fac[:, None, None] * at[None, :, None] * amp[None, None, :]
+    return par, m  # (n_columns, nz, 6)
+
+
+def hydro_tensor(order=4):
+    """polyfit of HydrodynamicKernelFunction(1e2 π) on the reference's grid (box_gamma_mixture_hydro.jl:22-23)."""
+    return CoalescenceTensor(polyfit(HydrodynamicKernelFunction(1e2 * math.pi), order, 1e-6, 0.0, NORMS))
+
+
+def c4_three_modes(n_parcels=1 << 24, seed=SEED0 + 4, last="gamma", empty_frac=0.02):
+    """C4: 3 modes (Gamma, Gamma, Gamma|Lognormal), order-4 hydrodynamic tensor, thresholds (1, 100, Inf) normalised
+    (box_gamma_mixture_3modes.jl:29, box_gamma_mixture_hydro.jl:22-23)."""
+    rng = np.random.default_rng(seed)
+    NProgMoms = (3, 3, 3)
+    last_kind = L.LOGNORMAL if last == "lognormal" else L.GAMMA
+    pd = (Gam(1e8, 1e-10, 1.0), Gam(0.0, 1e-8, 1.0), LogN(0.0, 1.0, 1.0) if last_kind == L.LOGNORMAL else Gam(0.0, 1e-6, 1.0))
+    cd = CoalescenceData(hydro_tensor(4), NProgMoms, (1e-9, 1e-7, math.inf), NORMS)
+    par = ModelParameters(pdists=pd, coal_data=cd, NProgMoms=NProgMoms, norms=NORMS, dt=1.0)
+    n1 = _logu(rng, 1e1, 1e3, n_parcels); th1 = _logu(rng, 0.03, 0.5, n_parcels); k1 = _logu(rng, 0.5, 5.0, n_parcels)
+    n2 = _logu(rng, 1e-4, 1e1, n_parcels); th2 = _logu(rng, 2.0, 40.0, n_parcels); k2 = _logu(rng, 0.5, 5.0, n_parcels)
+    n3 = _logu(rng, 1e-8, 1e-3, n_parcels)
+    if last_kind == L.LOGNORMAL:
+        mu3 = rng.uniform(math.log(100.0), math.log(1000.0), n_parcels); s3 = rng.uniform(0.3, 0.9, n_parcels)
+        m3 = _moments_from_params(L.LOGNORMAL, n3, mu3, s3, 3)
+    else:
+        th3 = _logu(rng, 100.0, 1000.0, n_parcels); k3 = _logu(rng, 0.5, 5.0, n_parcels)
+        m3 = _moments_from_params(L.GAMMA, n3, th3, k3, 3)
+    m = np.concatenate([_moments_from_params(L.GAMMA, n1, th1, k1, 3), _moments_from_params(L.GAMMA, n2, th2, k2, 3), m3], axis=1)
+    empty = rng.random(n_parcels) < empty_frac
+    m[empty, :] = 0.0
+    return par, m * _norm_factors(NProgMoms, NORMS)
+
+
+def long_kernel_two_modes(n_parcels=1024, seed=SEED0 + 44):
+    """Long-type variant: a matrix of P = 3 tensors (box_gamma_mixture_long.jl:21-36)."""
+    rng = np.random.default_rng(seed)
+    NProgMoms = (3, 3)
+    kf = LongKernelFunction(5.236e-10, 9.44e9, 5.78)
+    t11 = CoalescenceTensor(kf, 2, 5e-10)
+    tot = CoalescenceTensor(kf, 2, 1e-6, 5e-10)
+    kern = ((t11, tot), (tot, tot))
+    pd = (Gam(1e7, 1e-10, 1.0), Gam(1e5, 1e-9, 1.0))
+    cd = CoalescenceData(kern, NProgMoms, (5e-10, math.inf), NORMS)
+    par = ModelParameters(pdists=pd, coal_data=cd, NProgMoms=NProgMoms, norms=NORMS, dt=1.0)
+    n1 = _logu(rng, 1e0, 1e2, n_parcels); th1 = _logu(rng, 0.03, 0.3, n_parcels); k1 = _logu(rng, 0.5, 5.0, n_parcels)
+    n2 = _logu(rng, 1e-3, 1e0, n_parcels); th2 = _logu(rng, 0.5, 5.0, n_parcels); k2 = _logu(rng, 0.5, 5.0, n_parcels)
+    m = np.concatenate([_moments_from_params(L.GAMMA, n1, th1, k1, 3), _moments_from_params(L.GAMMA, n2, th2, k2, 3)], axis=1)
+    m[0] = np.array([1e7, 1e-3, 2e-13, 1e5, 1e-4, 2e-13]) / _norm_factors(NProgMoms, NORMS)
+    return par, m * _norm_factors(NProgMoms, NORMS)
+
+
+def mono_gamma(n_parcels=1024, seed=SEED0 + 45):
+    """Monodisperse + Gamma mixture (box_mono_gamma_mixture.jl:14-28)."""
+    rng = np.random.default_rng(seed)
+    NProgMoms = (2, 3)
+    pd = (Mono(1e7, 1e-10), Gam(1e5, 1e-9, 1.0))
+    cd = CoalescenceData(linear_tensor(5.0), NProgMoms, (5e-10, math.inf), NORMS)
+    par = ModelParameters(pdists=pd, coal_data=cd, NProgMoms=NProgMoms, norms=NORMS, dt=1.0)
+    n1 = _logu(rng, 1e0, 1e2, n_parcels); th1 = _logu(rng, 0.05, 0.6, n_parcels)
+    n2 = _logu(rng, 1e-3, 1e0, n_parcels); th2 = _logu(rng, 0.5, 5.0, n_parcels); k2 = _logu(rng, 0.5, 5.0, n_parcels)
+    m = np.concatenate([_moments_from_params(L.MONODISPERSE, n1, th1, None, 2), _moments_from_params(L.GAMMA, n2, th2, k2, 3)], axis=1)
+    m[0] = np.array([1e7, 1e-3, 1e5, 1e-4, 2e-13]) / _norm_factors(NProgMoms, NORMS)
+    return par, m * _norm_factors(NProgMoms, NORMS)
