@@ -1,0 +1,49 @@
+"""ctypes driver of oracle/liboracle.so (TEST INFRASTRUCTURE / CPU BASELINE ONLY — see cloudy_oracle.c)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liboracle.so")
+
+
+def build(force=False):
+    src = os.path.join(HERE, "cloudy_oracle.c")
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", HERE] + (["-B"] if force else []), check=True, capture_output=True)
+    return LIB
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        _lib = C.CDLL(LIB)
+        _lib.cloudy_oracle_rhs_coal_batch.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64, C.c_int]
+        _lib.cloudy_oracle_rhs_coal_batch.restype = C.c_int
+        _lib.cloudy_oracle_max_threads.restype = C.c_int
+        _lib.cloudy_oracle_moment_source_helper.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double,
+                                                            C.c_int, C.c_double, C.c_double]
+        _lib.cloudy_oracle_moment_source_helper.restype = C.c_double
+    return _lib
+
+
+def max_threads() -> int:
+    return load().cloudy_oracle_max_threads()
+
+
+def rhs_coal_batch(cfg_struct, states, n_threads=0):
+    """cfg_struct: the ctypes ``cloudy_config`` (same layout as include/cloudy_b200.h); states (n, n_slots)."""
+    a = np.ascontiguousarray(states, dtype=np.float64)
+    out = np.empty_like(a)
+    rc = load().cloudy_oracle_rhs_coal_batch(C.byref(cfg_struct), a.ctypes.data_as(C.POINTER(C.c_double)),
+                                             out.ctypes.data_as(C.POINTER(C.c_double)), a.shape[0], int(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle returned {rc}")
+    return out

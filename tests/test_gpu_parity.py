@@ -53,3 +53,164 @@ def test_c2_gamma_gamma(cb):
     kat = (-5623499.479946031, -3.975692677217648e-4, -6.433699758256767e-14, 623494.4299459805,
            3.975692677217648e-4, 2.6435719760256764e-13)  # SURVEY Appendix B KAT-D
     assert np.allclose(got[0], kat, rtol=1e-10, atol=0)
+
+
+def test_mono_gamma_and_long_kernel(cb):
+    from cloudy_b200 import workloads as W
+    for gen in (W.mono_gamma, W.long_kernel_two_modes):
+        par, state = gen(n_parcels=300)
+        _check_box(cb, par, state, 120, lanes=(4, 8))
+
+
+def test_c4_three_gamma_modes_order4(cb):
+    from cloudy_b200 import workloads as W
+    par, state = W.c4_three_modes(n_parcels=1000)
+    _check_box(cb, par, state, 60, lanes=(4, 8, 32))
+
+
+def test_ragged_and_empty_batches(cb):
+    """sizes that are not a multiple of the tile, a single parcel, and the empty batch"""
+    from cloudy_b200 import workloads as W
+    par, state = W.c2_gamma_exp(n_parcels=67)
+    full = _check_box(cb, par, state, 67)
+    model = cb.CoalescenceModel(par)
+    for n in (1, 31, 33):
+        got = model.coal_tendency_host(state[:n])
+        assert np.array_equal(got, full[:n])  # a parcel's result does not depend on its neighbours: bit-identical
+    assert model.coal_tendency_host(np.zeros((0, 5))).shape == (0, 5)
+
+
+def test_all_empty_and_extreme_parcels(cb):
+    """empty modes (n = 0 fallback), huge / tiny scale parameters, shape parameter at its clamps"""
+    from cloudy_b200 import workloads as W
+    par, _ = W.c2_gamma_exp(n_parcels=8)
+    nf = np.array([1e6, 1e-3, 1e-12, 1e6, 1e-3])
+    rows = [
+        [0, 0, 0, 0, 0],                       # everything empty
+        [100, 10, 2, 0, 0],                    # rain empty
+        [0, 0, 0, 1, 1],                       # cloud empty
+        [100, 10, 1.0000001, 1, 1],            # k clamps at 10 (variance ~ 0)
+        [100, 10, 1e6, 1, 1],                  # k tiny
+        [100, 1e-3, 2e-8, 1, 1],               # θ = 1e-5: threshold far in the tail (z up to 5e4)
+        [100, 1e4, 2e6, 1, 1],                 # θ = 100: threshold far below the mean
+        [1e-3, 1e-4, 2e-5, 1e-9, 1e-7],        # small numbers
+        [100, 60, 40, 1, 1],                   # X = x_th/θ around the series/continued-fraction switch
+        [100, 2.5, 0.07, 1, 1],
+    ]
+    state = np.array(rows, dtype=np.float64) * nf
+    _check_box(cb, par, state, len(rows), lanes=(4, 8, 16, 32))
+
+
+def test_full_size_properties(cb):
+    """BASELINE configs[1] at full size (1,048,576 parcels): size-independent properties — total mass tendency
+    cancels, number tendency is negative, permutation invariance, determinism."""
+    from cloudy_b200 import workloads as W
+    par, state = W.c2_gamma_exp()
+    model = cb.CoalescenceModel(par)
+    got = model.coal_tendency_host(state)
+    mass = got[:, 1] + got[:, 4]
+    scale = np.abs(got[:, 1]) + np.abs(got[:, 4]) + 1e-300
+    assert np.all(np.abs(mass) <= 1e-9 * scale + 1e-9 * np.abs(state[:, 1] + state[:, 4]))
+    assert np.all(got[:, 0] + got[:, 3] <= 0)
+    assert np.all(np.isfinite(got))
+    perm = np.random.default_rng(1).permutation(state.shape[0])
+    got_p = model.coal_tendency_host(state[perm])
+    assert np.array_equal(got_p, got[perm])
+    assert np.array_equal(model.coal_tendency_host(state), got)
+    # spot-check against the oracle across the ensemble
+    opar = oracle_params(par)
+    for i in range(0, state.shape[0], 16384):
+        ref, sc = O.rhs_coal(state[i], opar, return_scale=True)
+        ok, worst = tendency_close(got[i], ref, sc, RTOL)
+        assert ok, (i, worst)
+
+
+def test_sedimentation_flux_batched(cb):
+    from cloudy_b200 import workloads as W
+    par, cols = W.c3_rainshaft(n_columns=3, nz=16)
+    rng = np.random.default_rng(3)
+    state = cols.reshape(-1, 6).copy()
+    state[:, 3:] = state[:, :3] * rng.uniform(0.0, 1e-3, (state.shape[0], 1)) * np.array([1e-2, 1.0, 50.0])
+    model = cb.CoalescenceModel(par, nz=16)
+    u = model.ensemble(state.shape[0]).upload(state)
+    fl = model.ensemble(state.shape[0])
+    model.sedimentation_flux(u, fl)
+    got = fl.download()
+    opar = oracle_params(par)
+    for i in range(state.shape[0]):
+        ref = O.sedimentation_flux_state(state[i], opar)
+        assert np.allclose(got[i], ref, rtol=1e-12, atol=0), (i, got[i], ref)
+
+
+def _rain_state(cols, seed=5):
+    """give the rain mode some content and sprinkle negatives (the RHS clips them in place)"""
+    rng = np.random.default_rng(seed)
+    st = cols.copy()
+    st[..., 3:] = st[..., :3] * rng.uniform(0.0, 2e-3, st.shape[:-1] + (1,)) * np.array([1e-2, 1.0, 50.0])
+    neg = rng.random(st.shape) < 0.03
+    st[neg] = -np.abs(st[neg]) * 1e-3 - 1e-30
+    return st
+
+
+def test_c3_rainshaft_rhs(cb):
+    from cloudy_b200 import workloads as W
+    for nz, ncol in ((20, 3), (37, 2), (256, 1)):
+        par, cols = W.c3_rainshaft(n_columns=ncol, nz=nz)
+        st = _rain_state(cols)
+        rhs = cb.make_rainshaft_rhs(cb.AnalyticalCoalStyle())
+        m = st.copy()
+        got = rhs(m, par, 0.0)
+        opar = oracle_params(par)
+        for c in range(ncol):
+            mo = st[c].copy()
+            ref = O.rainshaft_rhs(mo, opar)
+            assert np.array_equal(m[c], mo)  # clipped in place, identically
+            scale = np.abs(ref) + np.abs(mo) * 50.0 / par.dz + 1e-300
+            assert np.all(np.abs(got[c] - ref) <= RTOL * scale), (nz, c, np.max(np.abs(got[c] - ref) / scale))
+
+
+def test_ssprk33_box_matches_oracle_run(cb):
+    """integrated moments rtol 1e-7 after the full run (north_star): box_gamma_mixture.jl, 12 steps of dt = 10"""
+    from cloudy_b200 import workloads as W
+    par, state = W.c2_gamma_gamma(n_parcels=40)
+    model = cb.CoalescenceModel(par)
+    u = model.ensemble(state.shape[0]).upload(state)
+    model.ssprk33_steps(u, par.dt, 12, cb.MODEL_BOX)
+    got = u.download()
+    opar = oracle_params(par)
+    for i in range(0, 40, 5):
+        ref = O.ssprk33(lambda m: O.rhs_coal(m, opar), state[i], par.dt, 12)
+        assert np.allclose(got[i], ref, rtol=1e-7, atol=0), (i, got[i], ref)
+    # odd and even step counts leave the result in the caller's ensemble
+    u2 = model.ensemble(state.shape[0]).upload(state)
+    model.ssprk33_steps(u2, par.dt, 5, cb.MODEL_BOX)
+    model.ssprk33_steps(u2, par.dt, 7, cb.MODEL_BOX)
+    assert np.allclose(u2.download(), got, rtol=1e-13, atol=0)
+
+
+def test_ssprk33_rainshaft_matches_oracle_run(cb):
+    from cloudy_b200 import workloads as W
+    par, cols = W.c3_rainshaft(n_columns=2, nz=20)
+    st = _rain_state(cols, seed=9)
+    model = cb.CoalescenceModel(par, nz=20)
+    flat = st.reshape(-1, 6)
+    u = model.ensemble(flat.shape[0]).upload(flat)
+    nsteps = 30
+    model.ssprk33_steps(u, par.dt, nsteps, cb.MODEL_RAINSHAFT)
+    got = u.download().reshape(st.shape)
+    opar = oracle_params(par)
+    for c in range(2):
+        ref = O.ssprk33(lambda m: O.rainshaft_rhs(m, opar), st[c], par.dt, nsteps)
+        ref[ref < 0] = 0  # the reference's FSAL evaluation clips the saved state (DESIGN.md)
+        scale = np.maximum(np.abs(ref), np.abs(ref).max(axis=0, keepdims=True) * 1e-6)
+        assert np.all(np.abs(got[c] - ref) <= 1e-7 * scale), np.max(np.abs(got[c] - ref) / scale)
+
+
+def test_moment_sums(cb):
+    from cloudy_b200 import workloads as W
+    par, state = W.c2_gamma_exp(n_parcels=100003)
+    model = cb.CoalescenceModel(par)
+    u = model.ensemble(state.shape[0]).upload(state)
+    got = model.moment_sums(u)
+    assert np.allclose(got, state.sum(axis=0), rtol=1e-12)
+    assert np.array_equal(got, model.moment_sums(u))  # deterministic
