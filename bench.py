@@ -170,7 +170,12 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream().cuda_stream
+    # a non-default torch stream is made current for the whole run and handed to the library, so that
+    # torch.cuda.Event timing brackets the library's launches (stream handle 0 would mean "private stream")
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     ctx = cb.Context(local, stream=stream)
     n = args.parcels
     par, state0 = workload(n, seed_offset=1000 * rank)

@@ -3,6 +3,7 @@ style tags in src/Sources/EquationTypes.jl.  The constructor logic (tensor norma
 N_2d_ints, threshold normalisation) runs on the host exactly as the reference's constructor does; the
 tendency evaluation itself is the CUDA kernel."""
 import ctypes as C
+import itertools
 import math
 from typing import Sequence, Tuple
 
@@ -22,6 +23,14 @@ class AnalyticalCoalStyle(CoalescenceStyle): ...
 class ThresholdStyle: ...
 class MovingThreshold(ThresholdStyle): ...
 class FixedThreshold(ThresholdStyle): ...
+
+
+_uid = itertools.count(1)
+
+
+def new_uid() -> int:
+    """Process-unique token for configuration caching (``id()`` values are recycled after garbage collection)."""
+    return next(_uid)
 
 
 def log_grid(x_threshold: float, n_bins_per_log_unit: int = 15):
@@ -64,6 +73,7 @@ class CoalescenceData:
         else:
             self.dist_thresholds = tuple(float(t) for t in dist_thresholds)
         self.norms = (float(norms[0]), float(norms[1]))
+        self.uid = new_uid()
 
 
 def build_config(kinds: Sequence[int], coal_data: CoalescenceData, norms=None, vel=(), dz: float = 1.0, nz: int = 1,
@@ -132,7 +142,7 @@ def get_coal_ints(cs, pdists, coal_data: CoalescenceData, ts: ThresholdStyle = N
     ctx = ctx or default_context()
     kinds = tuple(d.kind for d in pdists)
     cfg = build_config(kinds, coal_data, norms=(1.0, 1.0))
-    apply_config(ctx, cfg, key=("coal_ints", id(coal_data), kinds))
+    apply_config(ctx, cfg, key=("coal_ints", coal_data.uid, kinds))
     params = np.zeros((coal_data.N, 3))
     for i, d in enumerate(pdists):
         p = d.params()

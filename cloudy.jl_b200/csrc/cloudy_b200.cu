@@ -174,7 +174,7 @@ __device__ inline double moment_real(int kind, double n, double a, double b, dou
 template <int MPMAX, int LANES>
 __device__ __forceinline__ void node_integrals(double (&acc)[MPMAX * (MPMAX + 1) / 2], const double* __restrict__ tb, int nb, int M,
                                                int Mp, double k, double inv_th, double log_th, double gam_top,
-                                               const double* __restrict__ gtab, int deg_w, int cfd, int lane) {
+                                               const double* __restrict__ gtab, int deg_w, int cfd_w, int cfd, int lane) {
     constexpr int T = MPMAX * (MPMAX + 1) / 2;
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.0;
@@ -214,12 +214,12 @@ __device__ __forceinline__ void node_integrals(double (&acc)[MPMAX * (MPMAX + 1)
             const double zc = fmin(z, 256.0);  // beyond this the upper function is < 1e-80 of Gamma(a)
             double b = zc + 1.0 - a_top;
             double Pm = 1.0, Pc = b, Qm = 0.0, Qc = 1.0;
-            for (int n = 1; n <= cfd; ++n) {
-                const double an = -gtab[TAB_CF + n];  // -n(n-a) = n(a-n) negated
+            for (int n = 1; n <= cfd_w; ++n) {
+                const double an = -gtab[TAB_CF + n];  // -n(n-a)
                 b += 2.0;
                 const double Pn = fma(b, Pc, an * Pm);
                 const double Qn = fma(b, Qc, an * Qm);
-                Pm = Pc; Pc = Pn; Qm = Qc; Qc = Qn;
+                if (n <= cfd) { Pm = Pc; Pc = Pn; Qm = Qc; Qc = Qn; }  // own depth only (neighbour-independent result)
             }
             // E_top(zc): only differs from Etop when z > 256, where both are negligible
             const double up = Etop * (Qc / Pc);
@@ -420,14 +420,19 @@ __global__ void __launch_bounds__(Shape<LANES>::kThreads) rhs_kernel(const __gri
                     const double X = cfg.thr[md] * inv_th;
                     double zmax = fmin(X, a_top + (double)kSeriesMargin);
                     int zi = (zmax >= 0.0) ? (int)fmin(zmax, (double)(kSeriesTabLen - 1)) : 0;
-                    int deg = skip ? 1 : kSeriesDeg[zi];
+                    // a parcel's result must not depend on which parcels share its warp: the coefficient table is
+                    // built from the group's OWN degree (zero above it), only the loop bounds are warp maxima
+                    const int deg = skip ? 1 : kSeriesDeg[zi];
                     const int deg_w = __reduce_max_sync(0xffffffffu, deg);
                     int ai = (int)fmin(fmax(a_top, 0.0), 17.0);
-                    const int cfd_w = __reduce_max_sync(0xffffffffu, (int)kCfDepth[ai]);
-                    // series coefficients c_n = 1/(a)_{n+1}, n = 0..deg_w, chunked over the lanes:
+                    const int cfd = kCfDepth[ai];
+                    const int cfd_w = __reduce_max_sync(0xffffffffu, cfd);
+                    // series coefficients c_n = 1/(a)_{n+1}, n = 0..deg, chunked over the lanes:
                     // local product → group scan → one division → downward fill
                     {
-                        const int C = (deg_w + LANES) / LANES;  // chunk length, covers 0..deg_w
+                        for (int n = lane; n <= kSeriesMaxDeg; n += LANES) gtab[TAB_CT + n] = 0.0;
+                        __syncwarp();
+                        const int C = (deg + LANES) / LANES;  // chunk length, covers 0..deg
                         const int n0 = lane * C;
                         double prod = 1.0;
                         for (int i = 0; i < C; ++i) prod *= (a_top + (double)(n0 + i));
@@ -440,14 +445,15 @@ __global__ void __launch_bounds__(Shape<LANES>::kThreads) rhs_kernel(const __gri
                         double cc = 1.0 / incl;  // c at the top of my chunk: 1/(a)_{n0+C}
                         for (int i = C - 1; i >= 0; --i) {
                             const int n = n0 + i;
-                            if (n <= kSeriesMaxDeg) gtab[TAB_CT + n] = cc;
+                            if (n <= deg) gtab[TAB_CT + n] = cc;  // entries above the group's own degree stay zero
                             cc *= (a_top + (double)n);
                         }
-                        for (int i = lane; i < (Mp - 1) + cfd_w; i += LANES) {
+                        for (int i = lane; i < (Mp - 1) + kCfMaxDepth; i += LANES) {
                             if (i < Mp - 1) gtab[TAB_IA + i] = 1.0 / (k + (double)i);
                             else {
-                                const double fn = (double)(i - (Mp - 1) + 1);
-                                gtab[TAB_CF + (i - (Mp - 1) + 1)] = fn * (fn - a_top);
+                                const int nn = i - (Mp - 1) + 1;
+                                const double fn = (double)nn;
+                                gtab[TAB_CF + nn] = (nn <= cfd) ? fn * (fn - a_top) : 0.0;
                             }
                         }
                     }
@@ -456,7 +462,7 @@ __global__ void __launch_bounds__(Shape<LANES>::kThreads) rhs_kernel(const __gri
                     for (int p = 0; p < Mp - 1; ++p) gam_top *= (k + (double)p);  // Γ(k+Mp-1)
                     double acc[T];
                     node_integrals<(MPMAX > 0 ? MPMAX : 1), LANES>(acc, sTab + cfg.tab_off[md], cfg.n_bins[md], M, Mp, k, inv_th, log_th,
-                                                                  gam_top, gtab, deg_w, cfd_w, lane);
+                                                                  gam_top, gtab, deg_w, cfd_w, cfd, lane);
                     // F = 0 | min(Mom*Mom, H) — Coalescence.jl:212-227; H = n²θ^{p2}/Γ(k)² * Σ
                     const double* mom = my + L.mom + md * M;
                     const double pre0 = n_md * n_md * par[PAR_IGK2];

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib as L
 from .coalescence import (AnalyticalCoalStyle, CoalescenceData, FixedThreshold, MovingThreshold, apply_config,
-                          build_config)
+                          build_config, new_uid)
 from .context import Context, default_context
 from .distributions import nparams
 
@@ -79,7 +79,7 @@ class CoalescenceModel:
         self.nz = int(nz)
         self.cfg = build_config(self.kinds, par.coal_data, norms=par.norms, vel=getattr(par, "vel", ()),
                                 dz=getattr(par, "dz", 1.0), nz=self.nz)
-        self._key = ("model", id(self))
+        self._key = ("model", new_uid())
         self.n_slots = sum(self.NProgMoms)
         self.activate()
 
@@ -129,14 +129,14 @@ def make_box_model_rhs(coal_type, threshold_style=None):
     if not isinstance(coal_type, AnalyticalCoalStyle):
         raise ValueError("Invalid coal style!")
     threshold_style = threshold_style or FixedThreshold()
-    cache = {}
 
     def rhs(dm, m, par, t):
         if isinstance(threshold_style, MovingThreshold) != isinstance(par.coal_data.threshold_style, MovingThreshold):
             raise ValueError("threshold style does not match coal_data")
-        model = cache.get(id(par))
+        model = getattr(par, "_cloudy_model", None)  # cached on the parameter object itself (id() values are recycled)
         if model is None:
-            model = cache[id(par)] = CoalescenceModel(par)
+            model = CoalescenceModel(par)
+            par._cloudy_model = model
         a = np.atleast_2d(np.asarray(m, dtype=np.float64))
         out = model.coal_tendency_host(a)
         np.asarray(dm)[...] = out.reshape(np.shape(dm))
@@ -150,15 +150,16 @@ def make_rainshaft_rhs(coal_type):
     column (or (ncol, nz, nmom) columns); ``m`` is clipped at zero IN PLACE like the reference (:52)."""
     if not isinstance(coal_type, AnalyticalCoalStyle):
         raise ValueError("Invalid coal style!")
-    cache = {}
 
     def rhs(m, p, t):
         m = np.asarray(m)
         nz = m.shape[-2]
-        key = (id(p), nz)
-        model = cache.get(key)
+        models = getattr(p, "_cloudy_rain_models", None)
+        if models is None:
+            models = p._cloudy_rain_models = {}
+        model = models.get(nz)
         if model is None:
-            model = cache[key] = CoalescenceModel(p, nz=nz)
+            model = models[nz] = CoalescenceModel(p, nz=nz)
         flat = np.ascontiguousarray(m.reshape(-1, m.shape[-1]), dtype=np.float64)
         u = model.ensemble(flat.shape[0]).upload(flat)
         du = model.ensemble(flat.shape[0])

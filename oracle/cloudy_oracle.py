@@ -578,23 +578,29 @@ def sedimentation_flux_state(mom: Sequence[float], par: ModelParams):
     return get_sedimentation_flux(pd, vel_n) * np.array(mom_norms)
 
 
-def rainshaft_rhs(m: np.ndarray, par: ModelParams):
-    """rainshaft_helpers.jl:47-88. ``m`` is (nz, nmom) and is clipped IN PLACE like the reference (:52)."""
+def rainshaft_rhs(m: np.ndarray, par: ModelParams, return_scale: bool = False):
+    """rainshaft_helpers.jl:47-88. ``m`` is (nz, nmom) and is clipped IN PLACE like the reference (:52).
+    With ``return_scale`` also returns Σ|terms| per entry (coalescence terms + the two flux terms / dz)."""
     nz, nmom = m.shape
     m[m < 0] = 0
     coal = np.zeros_like(m)
+    cscale = np.zeros_like(m)
     flux = np.zeros((nz + 1, nmom))
     for i in range(nz):
         pd, mn, mom_norms = dists_from_state(m[i, :], par)
         if all(v < EPS for v in mn):
             coal[i, :] = 0.0
         else:
-            coal[i, :] = get_coal_ints(pd, par.cd) * np.array(mom_norms)
+            ci, sc = get_coal_ints(pd, par.cd, True)
+            coal[i, :] = ci * np.array(mom_norms)
+            cscale[i, :] = sc * np.array(mom_norms)
         vel_n = tuple((v * par.norms[1] ** b, b) for (v, b) in par.vel)
         flux[i, :] = get_sedimentation_flux(pd, vel_n) * np.array(mom_norms)
     sed = np.zeros_like(m)
     for i in range(nz):
         sed[i, :] = -(flux[i + 1, :] - flux[i, :]) / par.dz
+    if return_scale:
+        return coal + sed, cscale + (np.abs(flux[1:, :]) + np.abs(flux[:-1, :])) / par.dz
     return coal + sed
 
 
