@@ -76,6 +76,12 @@ struct KArgs {
 
 enum { MODEL_BOX = 0, MODEL_RAINSHAFT = 1 };
 
+// quadrature nodes each lane keeps in flight (independent Horner chains sharing the coefficient loads)
+template <int LANES>
+struct NodesPerLane {
+    static constexpr int value = (LANES <= 4) ? 4 : (LANES == 8 ? 2 : 1);
+};
+
 template <int LANES>
 struct Shape {
     static constexpr int kThreads = (LANES >= 8) ? 256 : 32 * LANES;
@@ -171,7 +177,7 @@ __device__ inline double moment_real(int kind, double n, double a, double b, dou
 // ------------------------------------------------------------------------------------------------
 // node loop: T accumulators of  sum_j W[p1][j] * g_j * gamma(k+p2, z_j),  p1 <= p2 < Mp
 // ------------------------------------------------------------------------------------------------
-template <int MPMAX, int LANES>
+template <int MPMAX, int LANES, int NPL>
 __device__ __forceinline__ void node_integrals(double (&acc)[MPMAX * (MPMAX + 1) / 2], const double* __restrict__ tb, int nb, int M,
                                                int Mp, double k, double inv_th, double log_th, double gam_top,
                                                const double* __restrict__ gtab, int deg_w, int cfd_w, int cfd, int lane) {
@@ -185,62 +191,103 @@ __device__ __forceinline__ void node_integrals(double (&acc)[MPMAX * (MPMAX + 1)
     const double* W = tb + 4 * nb;
     const double a_top = k + (double)(Mp - 1);
     const double ser_lim = a_top + (double)kSeriesMargin;
-    const int rounds = (nb + LANES - 1) / LANES;
-    for (int r = 0; r < rounds; ++r) {
-        int j = r * LANES + lane;
-        const bool valid = j < nb;
-        j = valid ? j : nb - 1;
-        const double u = XJ[j] * inv_th;
-        const double g = exp(fma(k, ELL[j] - log_th, -u));      // (x_j/θ)^k e^{-x_j/θ}
-        const double z = TMX[j] * inv_th;                        // (x_th - x_j)/θ
-        const double E = exp(fma(k, LZ[j] - log_th, -z));        // z^k e^{-z}
-        double zp[MPMAX];
-        zp[0] = 1.0;
+    const int batches = (nb + LANES * NPL - 1) / (LANES * NPL);
+    for (int bt = 0; bt < batches; ++bt) {
+        // NPL nodes per lane in flight: their Horner chains share every coefficient load and hide DFMA latency
+        int jj[NPL];
+        bool valid[NPL];
+        double z[NPL], gtop[NPL];
+        bool any_ser = false, any_cf = false;
 #pragma unroll
-        for (int p = 1; p < MPMAX; ++p) zp[p] = zp[p - 1] * z;
-        double Etop = E;
-#pragma unroll
-        for (int p = 1; p < MPMAX; ++p) Etop = (p < Mp) ? Etop * z : Etop;  // E * z^(Mp-1)
-        const bool use_ser = z < ser_lim;
-        double gam[MPMAX];
-        double gtop = 0.0;
-        if (__any_sync(0xffffffffu, use_ser)) {
-            double s = gtab[TAB_CT + deg_w];
-#pragma unroll 4
-            for (int n = deg_w - 1; n >= 0; --n) s = fma(s, z, gtab[TAB_CT + n]);
-            gtop = Etop * s;
+        for (int i = 0; i < NPL; ++i) {
+            const int j = (bt * NPL + i) * LANES + lane;
+            valid[i] = j < nb;
+            jj[i] = valid[i] ? j : nb - 1;
+            z[i] = TMX[jj[i]] * inv_th;  // (x_th - x_j)/θ
+            any_ser = any_ser || (z[i] < ser_lim);
+            any_cf = any_cf || !(z[i] < ser_lim);
+            gtop[i] = 0.0;
         }
-        if (__any_sync(0xffffffffu, !use_ser)) {
-            const double zc = fmin(z, 256.0);  // beyond this the upper function is < 1e-80 of Gamma(a)
-            double b = zc + 1.0 - a_top;
-            double Pm = 1.0, Pc = b, Qm = 0.0, Qc = 1.0;
+        if (__any_sync(0xffffffffu, any_ser)) {
+            double s[NPL];
+            const double c_top = gtab[TAB_CT + deg_w];
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) s[i] = c_top;
+            int n = deg_w - 1;
+            for (; n >= 3; n -= 4) {
+                const double c0 = gtab[TAB_CT + n], c1 = gtab[TAB_CT + n - 1], c2 = gtab[TAB_CT + n - 2], c3 = gtab[TAB_CT + n - 3];
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) s[i] = fma(s[i], z[i], c0);
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) s[i] = fma(s[i], z[i], c1);
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) s[i] = fma(s[i], z[i], c2);
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) s[i] = fma(s[i], z[i], c3);
+            }
+            for (; n >= 0; --n) {
+                const double c0 = gtab[TAB_CT + n];
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) s[i] = fma(s[i], z[i], c0);
+            }
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) gtop[i] = s[i];  // series sum; multiplied by E z^(Mp-1) below
+        }
+        if (__any_sync(0xffffffffu, any_cf)) {
+            // Legendre continued fraction of the upper function, forward recurrence, fixed depth
+            double Pm[NPL], Pc[NPL], Qm[NPL], Qc[NPL], b[NPL];
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) {
+                const double zc = fmin(z[i], 256.0);  // beyond this the upper function is < 1e-80 of Gamma(a)
+                b[i] = zc + 1.0 - a_top;
+                Pm[i] = 1.0; Pc[i] = b[i]; Qm[i] = 0.0; Qc[i] = 1.0;
+            }
             for (int n = 1; n <= cfd_w; ++n) {
                 const double an = -gtab[TAB_CF + n];  // -n(n-a)
-                b += 2.0;
-                const double Pn = fma(b, Pc, an * Pm);
-                const double Qn = fma(b, Qc, an * Qm);
-                if (n <= cfd) { Pm = Pc; Pc = Pn; Qm = Qc; Qc = Qn; }  // own depth only (neighbour-independent result)
+                const bool on = n <= cfd;             // own depth only (neighbour-independent result)
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) {
+                    b[i] += 2.0;
+                    const double Pn = fma(b[i], Pc[i], an * Pm[i]);
+                    const double Qn = fma(b[i], Qc[i], an * Qm[i]);
+                    if (on) { Pm[i] = Pc[i]; Pc[i] = Pn; Qm[i] = Qc[i]; Qc[i] = Qn; }
+                }
             }
-            // E_top(zc): only differs from Etop when z > 256, where both are negligible
-            const double up = Etop * (Qc / Pc);
-            if (!use_ser) gtop = gam_top - up;
+#pragma unroll
+            for (int i = 0; i < NPL; ++i)
+                if (!(z[i] < ser_lim)) gtop[i] = -(Qc[i] / Pc[i]);  // negative marks "upper function ratio"
         }
-        // downward recurrence to the lower orders
 #pragma unroll
-        for (int p = MPMAX - 1; p >= 0; --p) {
-            if (p == Mp - 1) gam[p] = gtop;
-            else if (p < Mp - 1) gam[p] = (gam[p + 1] + E * zp[p]) * gtab[TAB_IA + p];
-            else gam[p] = 0.0;
-        }
-        const double gv = valid ? g : 0.0;
-        int t = 0;
+        for (int i = 0; i < NPL; ++i) {
+            const int j = jj[i];
+            const double u = XJ[j] * inv_th;
+            const double g = exp(fma(k, ELL[j] - log_th, -u));     // (x_j/θ)^k e^{-x_j/θ}
+            const double E = exp(fma(k, LZ[j] - log_th, -z[i]));   // z^k e^{-z}
+            double zp[MPMAX];
+            zp[0] = 1.0;
 #pragma unroll
-        for (int p1 = 0; p1 < MPMAX; ++p1) {
-            const double wg = (p1 < Mp) ? W[p1 * nb + j] * gv : 0.0;
+            for (int p = 1; p < MPMAX; ++p) zp[p] = zp[p - 1] * z[i];
+            double Etop = E;
 #pragma unroll
-            for (int p2 = p1; p2 < MPMAX; ++p2) {
-                acc[t] = fma(wg, gam[p2], acc[t]);
-                ++t;
+            for (int p = 1; p < MPMAX; ++p) Etop = (p < Mp) ? Etop * z[i] : Etop;  // E * z^(Mp-1)
+            const double top = (z[i] < ser_lim) ? Etop * gtop[i] : fma(Etop, gtop[i], gam_top);
+            double gam[MPMAX];
+#pragma unroll
+            for (int p = MPMAX - 1; p >= 0; --p) {
+                if (p == Mp - 1) gam[p] = top;
+                else if (p < Mp - 1) gam[p] = (gam[p + 1] + E * zp[p]) * gtab[TAB_IA + p];
+                else gam[p] = 0.0;
+            }
+            const double gv = valid[i] ? g : 0.0;
+            int t = 0;
+#pragma unroll
+            for (int p1 = 0; p1 < MPMAX; ++p1) {
+                const double wg = (p1 < Mp) ? W[p1 * nb + j] * gv : 0.0;
+#pragma unroll
+                for (int p2 = p1; p2 < MPMAX; ++p2) {
+                    acc[t] = fma(wg, gam[p2], acc[t]);
+                    ++t;
+                }
             }
         }
     }
@@ -461,7 +508,7 @@ __global__ void __launch_bounds__(Shape<LANES>::kThreads) rhs_kernel(const __gri
                     double gam_top = par[PAR_GK];
                     for (int p = 0; p < Mp - 1; ++p) gam_top *= (k + (double)p);  // Γ(k+Mp-1)
                     double acc[T];
-                    node_integrals<(MPMAX > 0 ? MPMAX : 1), LANES>(acc, sTab + cfg.tab_off[md], cfg.n_bins[md], M, Mp, k, inv_th, log_th,
+                    node_integrals<(MPMAX > 0 ? MPMAX : 1), LANES, NodesPerLane<LANES>::value>(acc, sTab + cfg.tab_off[md], cfg.n_bins[md], M, Mp, k, inv_th, log_th,
                                                                   gam_top, gtab, deg_w, cfd_w, cfd, lane);
                     // F = 0 | min(Mom*Mom, H) — Coalescence.jl:212-227; H = n²θ^{p2}/Γ(k)² * Σ
                     const double* mom = my + L.mom + md * M;
