@@ -1,41 +1,66 @@
-"""Build recipe for libcloudy_b200.so (nvcc, sm_100a, in-tree)."""
+"""Build recipe for libcloudy_b200.so (nvcc, sm_100a, in-tree; translation units compiled in parallel)."""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "csrc", "cloudy_b200.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "special.cuh"), os.path.join(os.path.dirname(HERE), "include", "cloudy_b200.h")]
+CSRC = os.path.join(HERE, "csrc")
+UNITS = ["cloudy_b200.cu", "tpp_inst_A.cu", "tpp_inst_B.cu", "tpp_inst_C.cu", "tpp_inst_D.cu"]
+HEADERS = [os.path.join(CSRC, h) for h in ("special.cuh", "common.cuh", "tpp_kernel.cuh", "tpp_instances.inc")] + \
+          [os.path.join(os.path.dirname(HERE), "include", "cloudy_b200.h")]
 LIB = os.path.join(HERE, "libcloudy_b200.so")
+OBJDIR = os.path.join(CSRC, "build")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
 ]
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB):
+def _nvcc():
+    return os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
+def _obj(unit):
+    return os.path.join(OBJDIR, unit.replace(".cu", ".o"))
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for d in DEPS)
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _compile(unit):
+    src = os.path.join(CSRC, unit)
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-c", "-o", _obj(unit), src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    return unit, " ".join(cmd), res.returncode, res.stdout + res.stderr
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB, SRC]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    with open(os.path.join(HERE, "csrc", "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + log[-6000:])
+    os.makedirs(OBJDIR, exist_ok=True)
+    todo = [u for u in UNITS if force or _stale(_obj(u), [os.path.join(CSRC, u)] + HEADERS)]
+    logs = []
+    if todo:
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 1)) as ex:
+            for unit, cmd, rc, log in ex.map(_compile, todo):
+                logs.append(cmd + "\n" + log)
+                with open(os.path.join(OBJDIR, unit + ".log"), "w") as f:
+                    f.write(cmd + "\n" + log)
+                if rc != 0:
+                    raise RuntimeError(f"nvcc failed on {unit}:\n" + log[-6000:])
+    if todo or _stale(LIB, [_obj(u) for u in UNITS]):
+        cmd = [_nvcc(), "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [_obj(u) for u in UNITS]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(log)
+        print("\n".join(logs))
     return LIB
 
 

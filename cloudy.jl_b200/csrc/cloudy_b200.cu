@@ -27,54 +27,10 @@
 #include <vector>
 
 #include "../../include/cloudy_b200.h"
-#include "special.cuh"
+#include "common.cuh"
+#include "tpp_kernel.cuh"
 
 namespace cloudy {
-
-// ------------------------------------------------------------------------------------------------
-// device-side configuration (kernel parameter, lives in the constant bank)
-// ------------------------------------------------------------------------------------------------
-constexpr int MAXN = CLOUDY_MAX_MODES;
-constexpr int MAXP = CLOUDY_MAX_P;
-constexpr int MAXM = MAXP + 2;
-constexpr int MAXSLOT = CLOUDY_MAX_SLOTS;
-constexpr int MAXT = MAXM * (MAXM + 1) / 2;  // 28
-
-struct DevConfig {
-    int N, P, M, nslots;
-    int kind[MAXN], nprog[MAXN], slot0[MAXN];
-    int slot_mode[MAXSLOT], slot_order[MAXSLOT];
-    int thr_style, n_mom_max;
-    int n2d[MAXN], Mp[MAXN];       // Mp = min(M, n2d): orders 0..Mp-1 carry truncated integrals
-    int quad[MAXN];                // 1: Gamma/Exponential mode with finite threshold, not last → node loop
-    int mono_thr[MAXN];            // 1: Monodisperse mode with finite threshold, not last → closed form
-    int n_bins[MAXN], tab_off[MAXN];
-    int tab_total;                 // doubles of grid tables to stage in shared memory
-    int n_vel, nz;
-    double c[MAXN][MAXN][MAXP][MAXP];
-    double thr[MAXN];
-    double norm[MAXSLOT];
-    double k_lo, k_hi;
-    double velv[CLOUDY_MAX_VEL], velb[CLOUDY_MAX_VEL];  // v*norms[2]^beta, beta
-    double inv_dz_unused, dz;
-    const double* tab;  // device: per quad mode i at tab_off[i]: XJ[n] ELL[n] TMX[n] LZ[n] W[M][n]
-};
-
-struct KArgs {
-    const double* u_in;   // state the RHS is evaluated at
-    const double* u_n;    // u^n for stages 2,3 (nullptr otherwise)
-    double* out;          // tendency, flux or stage result
-    double* clip_back;    // rainshaft tendency call: clipped state written back (nullptr otherwise)
-    long long n;          // parcels / cells
-    long long s_in, s_n, s_out, s_clip;  // SoA strides (doubles)
-    double cn, ci, cf, dt, div;          // out = (cn*u_n + ci*u_in + cf*(dt*f))/div ; tend_only: out = f
-    int tend_only;
-    int flux_only;        // out = sedimentation flux (rainshaft_helpers.jl:77)
-    int params_in;        // u_in holds distribution parameters (n, θ|μ[, k|σ]) instead of moments; output not de-normalised
-    unsigned long long* err_count;
-};
-
-enum { MODEL_BOX = 0, MODEL_RAINSHAFT = 1 };
 
 // quadrature nodes each lane keeps in flight (independent Horner chains sharing the coefficient loads)
 template <int LANES>
@@ -116,62 +72,6 @@ __host__ __device__ inline GroupLayout group_layout(int N, int M, int nslots, bo
 
 __device__ __forceinline__ int tri_index(int p1, int p2, int Mcols) {  // p1 <= p2 < Mcols, row-major upper triangle
     return p1 * Mcols - (p1 * (p1 - 1)) / 2 + (p2 - p1);
-}
-
-// ------------------------------------------------------------------------------------------------
-// distribution parameters from normalised moments — ParticleDistributions.jl:456-541 — and the
-// moment matrix row of one mode — Coalescence.jl:187-198 / ParticleDistributions.jl:177-207
-// ------------------------------------------------------------------------------------------------
-struct ModeParams {
-    double n, a, b;  // (n, θ, k) or (n, μ, σ); b = 1 for Exponential/Monodisperse
-    int invalid;
-};
-
-__device__ inline ModeParams params_from_moments(int kind, double m0, double m1, double m2, double lo, double hi,
-                                                 double lo2 = kEps, double hi2 = INFINITY) {
-    ModeParams r;
-    r.invalid = 0;
-    if (kind == CLOUDY_GAMMA) {
-        if (m0 > kEps && m1 > kEps) {
-            r.n = m0;
-            double mean = m1 / m0;
-            double k = jl_max(lo, jl_min(hi, mean / (m2 / m1 - mean)));
-            r.b = k;
-            r.a = mean / k;
-        } else {
-            r.n = 0.0; r.a = 1.0; r.b = 1.0;
-        }
-    } else if (kind == CLOUDY_LOGNORMAL) {
-        if (m0 > kEps && m1 > kEps && m2 > kEps) {
-            // lo/hi clamp μ, lo2/hi2 clamp σ (reference defaults (-Inf, Inf), (eps, Inf))
-            double mu = jl_max(lo, jl_min(hi, log(m1 * m1 / (m0 * sqrt(m0)) / sqrt(m2))));
-            double arg = log(m0 * m2 / (m1 * m1));
-            if (arg < 0.0) r.invalid = 1;  // the reference throws a DomainError here (:498)
-            double sg = jl_max(lo2, jl_min(hi2, sqrt(arg)));
-            r.a = mu;
-            r.b = sg;
-            r.n = m1 / exp(mu + 0.5 * sg * sg);
-        } else {
-            r.n = 0.0; r.a = 1.0; r.b = 1.0;
-        }
-    } else {  // Exponential, Monodisperse
-        if (m0 > kEps && m1 > kEps) {
-            r.n = m0; r.a = m1 / m0; r.b = 1.0;
-        } else {
-            r.n = 0.0; r.a = 1.0; r.b = 1.0;
-        }
-    }
-    return r;
-}
-
-// moment(dist, q) for real q — ParticleDistributions.jl:177-207
-__device__ inline double moment_real(int kind, double n, double a, double b, double q) {
-    switch (kind) {
-        case CLOUDY_EXPONENTIAL: return n * pow(a, q) * tgamma(q + 1.0);
-        case CLOUDY_GAMMA: return n * pow(a, q) * tgamma(q + b) / tgamma(b);
-        case CLOUDY_MONODISPERSE: return n * pow(a, q);
-        default: return n * exp(q * a + q * q * b * b / 2);
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -789,6 +689,38 @@ __global__ void scalar_kernel(const ScalarArgs a) {
     }
 }
 
+// sedimentation flux of every cell, thread per cell — Sedimentation.jl:22-37 with the velocity normalisation of
+// rainshaft_helpers.jl:74-77.  moment(dist, q+β) for q = 0,1,2 follows from the q = 0 value by Γ(x+1) = xΓ(x).
+__global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevConfig cfg, const KArgs args) {
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < args.n; p += (long long)gridDim.x * blockDim.x) {
+        for (int i = 0; i < cfg.N; ++i) {
+            const int s0 = cfg.slot0[i], np = cfg.nprog[i], kind = cfg.kind[i];
+            double mn[3] = {0.0, 0.0, 0.0};
+            for (int q = 0; q < np; ++q) {
+                double v = args.u_in[(s0 + q) * args.s_in + p];
+                v = (v < 0.0) ? 0.0 : v;  // rainshaft_helpers.jl:52
+                mn[q] = v / cfg.norm[s0 + q];
+            }
+            const ModeParams mp = params_from_moments(kind, mn[0], mn[1], mn[2], kind == CLOUDY_GAMMA ? cfg.k_lo : -INFINITY,
+                                                      kind == CLOUDY_GAMMA ? cfg.k_hi : INFINITY);
+            double fl[3] = {0.0, 0.0, 0.0};
+            for (int v = 0; v < cfg.n_vel; ++v) {
+                const double beta = cfg.velb[v];
+                double mq = 0.0;
+                if (mp.n != 0.0 && kind != CLOUDY_LOGNORMAL) mq = moment_real(kind, mp.n, mp.a, mp.b, beta);
+                for (int q = 0; q < np; ++q) {
+                    if (kind == CLOUDY_LOGNORMAL) mq = (mp.n != 0.0) ? moment_real(kind, mp.n, mp.a, mp.b, (double)q + beta) : 0.0;
+                    fl[q] += -cfg.velv[v] * mq;
+                    if (kind == CLOUDY_GAMMA) mq *= mp.a * (mp.b + beta + q);
+                    else if (kind == CLOUDY_EXPONENTIAL) mq *= mp.a * (beta + q + 1.0);
+                    else mq *= mp.a;
+                }
+            }
+            for (int q = 0; q < np; ++q) args.out[(s0 + q) * args.s_out + p] = fl[q] * cfg.norm[s0 + q];
+        }
+    }
+}
+
 // FP64 peak: independent FMA chains
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -840,9 +772,24 @@ struct cloudy_ctx {
     double* d_partial;
     double* d_scratch;     // small device scratch for scalar entry points
     cloudy_state* tmp[3];  // stepper / host-path work buffers
+    cloudy_state* flux;    // rainshaft: per-cell sedimentation flux for the thread-per-parcel kernel
     double* d_stage_aos;   // staging for upload/download
     long long stage_cap;
 };
+
+namespace cloudy {
+tpp_fn tpp_lookup_A(int, int, int);
+tpp_fn tpp_lookup_B(int, int, int);
+tpp_fn tpp_lookup_C(int, int, int);
+tpp_fn tpp_lookup_D(int, int, int);
+tpp_fn tpp_lookup(int N, int P, int model) {
+    tpp_fn f = tpp_lookup_A(N, P, model);
+    if (!f) f = tpp_lookup_B(N, P, model);
+    if (!f) f = tpp_lookup_C(N, P, model);
+    if (!f) f = tpp_lookup_D(N, P, model);
+    return f;
+}
+}  // namespace cloudy
 
 typedef void (*rhs_fn)(const DevConfig, const KArgs);
 struct KernelEntry {
@@ -873,9 +820,56 @@ static KernelEntry pick_lanes(int lanes, int mpmax) {
     }
 }
 
+extern "C" {
+static int ensure_flux(cloudy_ctx* ctx, long long n);
+}
+
+static int launch_flux(cloudy_ctx* ctx, const KArgs& args) {
+    long long blocks = std::min<long long>((args.n + 255) / 256, (long long)ctx->sm_count * 8);
+    void* params[2] = {(void*)&ctx->dev, (void*)&args};
+    CUDA_TRY(cudaLaunchKernel((const void*)flux_kernel, dim3((unsigned)std::max<long long>(blocks, 1)), dim3(256), params, 0, ctx->stream));
+    ctx->launches++;
+    return CLOUDY_OK;
+}
+
+static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
+    const DevConfig& d = ctx->dev;
+    if (args.flux_only) return launch_flux(ctx, args);
+    if (model == CLOUDY_MODEL_RAINSHAFT) {
+        int rc = ensure_flux(ctx, args.n);
+        if (rc) return rc;
+        KArgs fa = args;
+        fa.out = ctx->flux->d;
+        fa.s_out = ctx->flux->stride;
+        if ((rc = launch_flux(ctx, fa))) return rc;
+        args.flux = ctx->flux->d;
+        args.s_flux = ctx->flux->stride;
+    }
+    size_t smem = sizeof(double) * (((size_t)d.tab_total + 1) / 2 * 2 + (size_t)TPP_CT_ROWS * TPP_THREADS);
+    CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, TPP_THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long n_blocks = (args.n + TPP_THREADS - 1) / TPP_THREADS;
+    long long grid = std::min<long long>(n_blocks, (long long)ctx->sm_count * per_sm);
+    if (grid < 1) grid = 1;
+    void* params[2] = {(void*)&ctx->dev, (void*)&args};
+    CUDA_TRY(cudaLaunchKernel((const void*)fn, dim3((unsigned)grid), dim3(TPP_THREADS), params, smem, ctx->stream));
+    ctx->launches++;
+    return CLOUDY_OK;
+}
+
 static int launch_rhs(cloudy_ctx* ctx, int model, const KArgs& args) {
-    KernelEntry ke = (model == CLOUDY_MODEL_RAINSHAFT) ? pick_lanes<MODEL_RAINSHAFT>(ctx->lanes, ctx->mpmax)
-                                                       : pick_lanes<MODEL_BOX>(ctx->lanes, ctx->mpmax);
+    // lanes == 0: thread-per-parcel kernel when the (N, P) shape has an instance, else the lane-cooperative kernel (8 lanes);
+    // lanes == 1: thread-per-parcel required; lanes in {4, 8, 16, 32}: lane-cooperative kernel
+    if (ctx->lanes <= 1) {
+        tpp_fn fn = tpp_lookup(ctx->dev.N, ctx->dev.P, model == CLOUDY_MODEL_RAINSHAFT ? MODEL_RAINSHAFT : MODEL_BOX);
+        if (fn) return launch_tpp(ctx, fn, model, args);
+        if (ctx->lanes == 1) return fail(CLOUDY_ERR_UNSUPPORTED, "no thread-per-parcel kernel instance for this (n_modes, P)");
+    }
+    const int lanes = ctx->lanes <= 1 ? 8 : ctx->lanes;
+    KernelEntry ke = (model == CLOUDY_MODEL_RAINSHAFT) ? pick_lanes<MODEL_RAINSHAFT>(lanes, ctx->mpmax)
+                                                       : pick_lanes<MODEL_BOX>(lanes, ctx->mpmax);
     const DevConfig& d = ctx->dev;
     const bool rain = (model == CLOUDY_MODEL_RAINSHAFT);
     GroupLayout L = group_layout(d.N, d.M, d.nslots, rain);
@@ -916,7 +910,7 @@ int cloudy_ctx_create(int device, void* stream, cloudy_ctx** out) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
-    c->lanes = 8;
+    c->lanes = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaMalloc(&c->d_err, sizeof(unsigned long long)));
     CUDA_TRY(cudaMemset(c->d_err, 0, sizeof(unsigned long long)));
@@ -932,6 +926,7 @@ int cloudy_ctx_destroy(cloudy_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 3; ++i)
         if (ctx->tmp[i]) cloudy_state_destroy(ctx->tmp[i]);
+    if (ctx->flux) cloudy_state_destroy(ctx->flux);
     cudaFree(ctx->d_tab);
     cudaFree(ctx->d_err);
     cudaFree(ctx->d_partial);
@@ -944,8 +939,8 @@ int cloudy_ctx_destroy(cloudy_ctx* ctx) {
 
 int cloudy_set_lanes(cloudy_ctx* ctx, int lanes) {
     if (!ctx) return fail(CLOUDY_ERR_ARG, "ctx is NULL");
-    if (lanes == 0) lanes = 8;
-    if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return fail(CLOUDY_ERR_ARG, "lanes must be 4, 8, 16 or 32");
+    if (lanes != 0 && lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
+        return fail(CLOUDY_ERR_ARG, "lanes must be 0 (auto), 1 (thread per parcel), 4, 8, 16 or 32");
     ctx->lanes = lanes;
     return CLOUDY_OK;
 }
@@ -1065,6 +1060,7 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
     ctx->configured = true;
     for (int i = 0; i < 3; ++i)
         if (ctx->tmp[i]) { cloudy_state_destroy(ctx->tmp[i]); ctx->tmp[i] = nullptr; }
+    if (ctx->flux) { cloudy_state_destroy(ctx->flux); ctx->flux = nullptr; }
     return CLOUDY_OK;
 }
 
@@ -1211,6 +1207,12 @@ int cloudy_rainshaft_rhs(cloudy_ctx* ctx, cloudy_state* m, cloudy_state* dm) {
     a.clip_back = m->d;
     a.s_clip = m->stride;
     return launch_rhs(ctx, CLOUDY_MODEL_RAINSHAFT, a);
+}
+
+static int ensure_flux(cloudy_ctx* ctx, long long n) {
+    if (ctx->flux && ctx->flux->n == n) return CLOUDY_OK;
+    if (ctx->flux) { cloudy_state_destroy(ctx->flux); ctx->flux = nullptr; }
+    return cloudy_state_create(ctx, n, &ctx->flux);
 }
 
 static int ensure_tmp(cloudy_ctx* ctx, int idx, long long n) {

@@ -1,0 +1,118 @@
+// Shared device-side definitions of libcloudy_b200: run-constant configuration, kernel arguments and the
+// per-mode closed forms (parameters from moments, moments from parameters).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/cloudy_b200.h"
+#include "special.cuh"
+
+namespace cloudy {
+
+// ------------------------------------------------------------------------------------------------
+// device-side configuration (kernel parameter, lives in the constant bank)
+// ------------------------------------------------------------------------------------------------
+constexpr int MAXN = CLOUDY_MAX_MODES;
+constexpr int MAXP = CLOUDY_MAX_P;
+constexpr int MAXM = MAXP + 2;
+constexpr int MAXSLOT = CLOUDY_MAX_SLOTS;
+constexpr int MAXT = MAXM * (MAXM + 1) / 2;  // 28
+
+struct DevConfig {
+    int N, P, M, nslots;
+    int kind[MAXN], nprog[MAXN], slot0[MAXN];
+    int slot_mode[MAXSLOT], slot_order[MAXSLOT];
+    int thr_style, n_mom_max;
+    int n2d[MAXN], Mp[MAXN];       // Mp = min(M, n2d): orders 0..Mp-1 carry truncated integrals
+    int quad[MAXN];                // 1: Gamma/Exponential mode with finite threshold, not last → node loop
+    int mono_thr[MAXN];            // 1: Monodisperse mode with finite threshold, not last → closed form
+    int n_bins[MAXN], tab_off[MAXN];
+    int tab_total;                 // doubles of grid tables to stage in shared memory
+    int n_vel, nz;
+    double c[MAXN][MAXN][MAXP][MAXP];
+    double thr[MAXN];
+    double norm[MAXSLOT];
+    double k_lo, k_hi;
+    double velv[CLOUDY_MAX_VEL], velb[CLOUDY_MAX_VEL];  // v*norms[2]^beta, beta
+    double inv_dz_unused, dz;
+    const double* tab;  // device: per quad mode i at tab_off[i]: XJ[n] ELL[n] TMX[n] LZ[n] W[M][n]
+};
+
+struct KArgs {
+    const double* u_in;   // state the RHS is evaluated at
+    const double* u_n;    // u^n for stages 2,3 (nullptr otherwise)
+    double* out;          // tendency, flux or stage result
+    double* clip_back;    // rainshaft tendency call: clipped state written back (nullptr otherwise)
+    long long n;          // parcels / cells
+    long long s_in, s_n, s_out, s_clip;  // SoA strides (doubles)
+    double cn, ci, cf, dt, div;          // out = (cn*u_n + ci*u_in + cf*(dt*f))/div ; tend_only: out = f
+    int tend_only;
+    int flux_only;        // out = sedimentation flux (rainshaft_helpers.jl:77)
+    int params_in;        // u_in holds distribution parameters (n, θ|μ[, k|σ]) instead of moments; output not de-normalised
+    unsigned long long* err_count;
+    // thread-per-parcel kernels only
+    const int* perm;      // processing order (regime-sorted parcel indices) or nullptr for identity
+    const double* flux;   // rainshaft: per-cell sedimentation flux (SoA like the state), written by flux_kernel
+    long long s_flux;
+};
+
+enum { MODEL_BOX = 0, MODEL_RAINSHAFT = 1 };
+
+// ------------------------------------------------------------------------------------------------
+// distribution parameters from normalised moments — ParticleDistributions.jl:456-541 — and the
+// moment matrix row of one mode — Coalescence.jl:187-198 / ParticleDistributions.jl:177-207
+// ------------------------------------------------------------------------------------------------
+struct ModeParams {
+    double n, a, b;  // (n, θ, k) or (n, μ, σ); b = 1 for Exponential/Monodisperse
+    int invalid;
+};
+
+__device__ inline ModeParams params_from_moments(int kind, double m0, double m1, double m2, double lo, double hi,
+                                                 double lo2 = kEps, double hi2 = INFINITY) {
+    ModeParams r;
+    r.invalid = 0;
+    if (kind == CLOUDY_GAMMA) {
+        if (m0 > kEps && m1 > kEps) {
+            r.n = m0;
+            double mean = m1 / m0;
+            double k = jl_max(lo, jl_min(hi, mean / (m2 / m1 - mean)));
+            r.b = k;
+            r.a = mean / k;
+        } else {
+            r.n = 0.0; r.a = 1.0; r.b = 1.0;
+        }
+    } else if (kind == CLOUDY_LOGNORMAL) {
+        if (m0 > kEps && m1 > kEps && m2 > kEps) {
+            // lo/hi clamp μ, lo2/hi2 clamp σ (reference defaults (-Inf, Inf), (eps, Inf))
+            double mu = jl_max(lo, jl_min(hi, log(m1 * m1 / (m0 * sqrt(m0)) / sqrt(m2))));
+            double arg = log(m0 * m2 / (m1 * m1));
+            if (arg < 0.0) r.invalid = 1;  // the reference throws a DomainError here (:498)
+            double sg = jl_max(lo2, jl_min(hi2, sqrt(arg)));
+            r.a = mu;
+            r.b = sg;
+            r.n = m1 / exp(mu + 0.5 * sg * sg);
+        } else {
+            r.n = 0.0; r.a = 1.0; r.b = 1.0;
+        }
+    } else {  // Exponential, Monodisperse
+        if (m0 > kEps && m1 > kEps) {
+            r.n = m0; r.a = m1 / m0; r.b = 1.0;
+        } else {
+            r.n = 0.0; r.a = 1.0; r.b = 1.0;
+        }
+    }
+    return r;
+}
+
+// moment(dist, q) for real q — ParticleDistributions.jl:177-207
+__device__ inline double moment_real(int kind, double n, double a, double b, double q) {
+    switch (kind) {
+        case CLOUDY_EXPONENTIAL: return n * pow(a, q) * tgamma(q + 1.0);
+        case CLOUDY_GAMMA: return n * pow(a, q) * tgamma(q + b) / tgamma(b);
+        case CLOUDY_MONODISPERSE: return n * pow(a, q);
+        default: return n * exp(q * a + q * q * b * b / 2);
+    }
+}
+
+}  // namespace cloudy

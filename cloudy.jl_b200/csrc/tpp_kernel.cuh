@@ -1,0 +1,438 @@
+// Thread-per-parcel kernel (the fast path for the mode/tensor shapes listed in tpp_instances.cu).
+//
+// One thread evaluates one parcel's (or one column cell's) coalescence tendency end to end:
+//   rhs_coal!                test/examples/utils/box_model_helpers.jl:29-53
+//   get_coal_ints            src/Sources/Coalescence.jl:115-150 (+ :187-455 underneath)
+//   update_dist_from_moments src/ParticleDistributions/ParticleDistributions.jl:456-541
+//   moment_source_helper     src/ParticleDistributions/ParticleDistributions.jl:567-612 (+ Simpson :698-710)
+// with everything that is per-parcel (distribution parameters, moment matrix, truncated integrals F, the
+// Q/R/S contraction) held in registers — N (modes) and P (tensor size) are template parameters so every
+// loop over them unrolls.  All threads of a warp walk the SAME quadrature nodes at the same time, so the
+// node tables are shared-memory broadcasts; the only per-thread table is the parcel's series coefficients
+// c_n = 1/(a)_{n+1} (column `tid` of a [64][threads] shared array, conflict-free).  NPL nodes are in flight
+// per thread: their Horner chains share each coefficient load and hide the DFMA latency.
+// Warps are made homogeneous (similar series length, same series/continued-fraction regime) by an optional
+// regime sort of the parcel order (args.perm).
+#pragma once
+#include "common.cuh"
+
+namespace cloudy {
+
+constexpr int TPP_THREADS = 128;
+constexpr int TPP_NPL = 5;       // 75 nodes (every threshold <= 1 in normalised units) = 15 batches exactly
+constexpr int TPP_CT_ROWS = 64;  // series coefficients c_0..c_63
+
+__host__ __device__ constexpr int tri_ct(int p1, int p2, int MP) { return p1 * MP - (p1 * (p1 - 1)) / 2 + (p2 - p1); }
+
+// ------------------------------------------------------------------------------------------------
+// node loop for one mode of one parcel: acc[t(p1,p2)] = sum_j W[p1][j] g_j gamma(k+p2, z_j)
+// ------------------------------------------------------------------------------------------------
+template <int MP>
+__device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], const double* __restrict__ tb, const int nb, const double k,
+                                          const double inv_th, const double log_th, const double gam_top, const double (&ia)[MP],
+                                          const double* __restrict__ myCt, const int deg_w, const int cfd_w, const int cfd,
+                                          const double a_top) {
+    constexpr int T = MP * (MP + 1) / 2;
+    constexpr int NPL = TPP_NPL;
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[t] = 0.0;
+    const double* XJ = tb;
+    const double* ELL = tb + nb;
+    const double* TMX = tb + 2 * nb;
+    const double* LZ = tb + 3 * nb;
+    const double* W = tb + 4 * nb;
+    const double ser_lim = a_top + (double)kSeriesMargin;
+    for (int j0 = 0; j0 < nb; j0 += NPL) {
+        double z[NPL], gtop[NPL];
+        bool any_ser = false, any_cf = false;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            const int j = min(j0 + i, nb - 1);
+            z[i] = TMX[j] * inv_th;  // (x_th - x_j)/θ
+            any_ser = any_ser || (z[i] < ser_lim);
+            any_cf = any_cf || !(z[i] < ser_lim);
+            gtop[i] = 0.0;
+        }
+        if (__any_sync(0xffffffffu, any_ser)) {
+            // series: gamma(a,z) = z^a e^-z * sum_n c_n z^n, Horner from the warp's largest degree (own table is
+            // zero above the parcel's own degree, so the result does not depend on the neighbours)
+            double s[NPL];
+            const double c_top = myCt[deg_w * TPP_THREADS];
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) s[i] = c_top;
+            int n = deg_w - 1;
+            for (; n >= 3; n -= 4) {
+                const double c0 = myCt[n * TPP_THREADS], c1 = myCt[(n - 1) * TPP_THREADS], c2 = myCt[(n - 2) * TPP_THREADS],
+                             c3 = myCt[(n - 3) * TPP_THREADS];
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) s[i] = fma(s[i], z[i], c0);
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) s[i] = fma(s[i], z[i], c1);
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) s[i] = fma(s[i], z[i], c2);
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) s[i] = fma(s[i], z[i], c3);
+            }
+            for (; n >= 0; --n) {
+                const double c0 = myCt[n * TPP_THREADS];
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) s[i] = fma(s[i], z[i], c0);
+            }
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) gtop[i] = s[i];
+        }
+        if (__any_sync(0xffffffffu, any_cf)) {
+            // Legendre continued fraction of Gamma(a,z)/(z^a e^-z), forward recurrence, fixed depth.  Beyond the
+            // parcel's own depth the step degenerates to P <- 1*P + 0, which is exact.
+            double Pm[NPL], Pc[NPL], Qm[NPL], Qc[NPL], b[NPL];
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) {
+                const double zc = fmin(z[i], 256.0);  // beyond this the upper function is < 1e-80 of Gamma(a)
+                b[i] = zc + 1.0 - a_top;
+                Pm[i] = 1.0; Pc[i] = b[i]; Qm[i] = 0.0; Qc[i] = 1.0;
+            }
+            double fn = 0.0;
+            for (int n = 1; n <= cfd_w; ++n) {
+                fn += 1.0;
+                const bool on = n <= cfd;
+                const double an = on ? fn * (a_top - fn) : 0.0;  // -n(n-a)
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) {
+                    b[i] += 2.0;
+                    const double bb = on ? b[i] : 1.0;
+                    const double Pn = fma(bb, Pc[i], an * Pm[i]);
+                    const double Qn = fma(bb, Qc[i], an * Qm[i]);
+                    Pm[i] = Pc[i]; Pc[i] = Pn; Qm[i] = Qc[i]; Qc[i] = Qn;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NPL; ++i)
+                if (!(z[i] < ser_lim)) gtop[i] = -(Qc[i] / Pc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+            const int jraw = j0 + i;
+            const int j = min(jraw, nb - 1);
+            const double u = XJ[j] * inv_th;
+            const double g = exp(fma(k, ELL[j] - log_th, -u));    // (x_j/θ)^k e^{-x_j/θ}
+            const double E = exp(fma(k, LZ[j] - log_th, -z[i]));  // z^k e^{-z}
+            double zp[MP];
+            zp[0] = 1.0;
+#pragma unroll
+            for (int p = 1; p < MP; ++p) zp[p] = zp[p - 1] * z[i];
+            const double Etop = E * zp[MP - 1];
+            double gam[MP];
+            gam[MP - 1] = (z[i] < ser_lim) ? Etop * gtop[i] : fma(Etop, gtop[i], gam_top);
+#pragma unroll
+            for (int p = MP - 2; p >= 0; --p) gam[p] = (gam[p + 1] + E * zp[p]) * ia[p];  // downward recurrence
+            const double gv = (jraw < nb) ? g : 0.0;
+            int t = 0;
+#pragma unroll
+            for (int p1 = 0; p1 < MP; ++p1) {
+                const double wg = W[p1 * nb + j] * gv;
+#pragma unroll
+                for (int p2 = p1; p2 < MP; ++p2) {
+                    acc[t] = fma(wg, gam[p2], acc[t]);
+                    ++t;
+                }
+            }
+        }
+    }
+}
+
+// S_1k and S_2k of one mode, all orders m < 3 — Coalescence.jl:353-455.  F(x,y) is supplied by a functor.
+template <int P, typename FGet>
+__device__ __forceinline__ void tpp_s_terms(const DevConfig& cfg, const int k, const double (&momk)[P + 2], FGet F, double (&s1)[3], double (&s2)[3]) {
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < P; ++a) {
+            double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+            for (int b = 0; b < P; ++b) {
+                const double hc = 0.5 * cfg.c[k][k][a][b];
+                double c1 = 0.0, c2 = 0.0;
+#pragma unroll
+                for (int c = 0; c <= m; ++c) {
+                    const double h = (m == 2 && c == 1) ? hc * 2.0 : hc;  // 0.5 * c_ab * binomial(m, c)
+                    const double f = F(a + c, b + m - c);
+                    c1 = fma(h, f, c1);
+                    c2 = fma(h, momk[a + c] * momk[b + m - c] - f, c2);
+                }
+                b1 += c1;
+                b2 += c2;
+            }
+            a1 += b1;
+            a2 += b2;
+        }
+        s1[m] = a1;
+        s2[m] = a2;
+    }
+}
+
+struct TppShared {
+    int deg[kSeriesTabLen];
+    int cfd[18];
+};
+
+template <int N, int P, int MODEL>
+__global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant__ DevConfig cfg, const KArgs args) {
+    constexpr int M = P + 2;
+    constexpr bool RAIN = (MODEL == MODEL_RAINSHAFT);
+    extern __shared__ double smem[];
+    __shared__ TppShared sh;
+    double* sTab = smem;
+    double* sCt = smem + ((cfg.tab_total + 1) & ~1);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < cfg.tab_total; i += TPP_THREADS) sTab[i] = cfg.tab[i];
+    if (tid < kSeriesTabLen) sh.deg[tid] = kSeriesDeg[tid];
+    if (tid < 18) sh.cfd[tid] = kCfDepth[tid];
+    __syncthreads();
+    const double* myCtc = sCt + tid;
+    double* myCt = sCt + tid;
+
+    const long long n = args.n;
+    for (long long base = blockIdx.x * (long long)TPP_THREADS + (tid & ~31); base < n; base += (long long)gridDim.x * TPP_THREADS) {
+        const long long idx = base + (tid & 31);
+        const bool live = idx < n;
+        const long long qi = live ? idx : n - 1;
+        const long long p = (args.perm != nullptr) ? (long long)args.perm[qi] : qi;
+
+        // ---- load, (clip), normalise, parameters, moment matrix --------------------------------------
+        double raw[N][3];
+        double mom[N][M];
+        double pn[N], pa[N], pb[N];
+        bool cell_empty = RAIN;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int s0 = cfg.slot0[i], np = cfg.nprog[i], kind = cfg.kind[i];
+            double mn[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                raw[i][q] = 0.0;
+                if (q < np) {
+                    double v = args.u_in[(s0 + q) * args.s_in + p];
+                    if (RAIN) {
+                        v = (v < 0.0) ? 0.0 : v;  // rainshaft_helpers.jl:52
+                        if (args.clip_back != nullptr && live) args.clip_back[(s0 + q) * args.s_clip + p] = v;
+                    }
+                    raw[i][q] = v;
+                    mn[q] = v / cfg.norm[s0 + q];
+                    if (RAIN) cell_empty = cell_empty && (mn[q] < kEps);  // rainshaft_helpers.jl:67
+                }
+            }
+            ModeParams mp;
+            if (args.params_in) {
+                mp.n = raw[i][0]; mp.a = raw[i][1]; mp.b = (np > 2) ? raw[i][2] : 1.0; mp.invalid = 0;
+            } else {
+                mp = params_from_moments(kind, mn[0], mn[1], mn[2], kind == CLOUDY_GAMMA ? cfg.k_lo : -INFINITY,
+                                         kind == CLOUDY_GAMMA ? cfg.k_hi : INFINITY);
+            }
+            if (mp.invalid && live && args.err_count != nullptr) atomicAdd(args.err_count, 1ULL);
+            pn[i] = mp.n; pa[i] = mp.a; pb[i] = mp.b;
+            double mq = mp.n;
+#pragma unroll
+            for (int q = 0; q < M; ++q) {  // Coalescence.jl:187-198
+                double val = mq;
+                if (kind == CLOUDY_LOGNORMAL) val = mp.n * exp(q * mp.a + (double)(q * q) * mp.b * mp.b / 2);
+                mom[i][q] = (q < cfg.n_mom_max) ? val : 0.0;
+                if (kind == CLOUDY_GAMMA) mq *= mp.a * (mp.b + q);
+                else if (kind == CLOUDY_EXPONENTIAL) mq *= mp.a * (q + 1.0);
+                else mq *= mp.a;
+            }
+        }
+
+        double res[N][3];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) res[i][q] = 0.0;
+
+        // ---- S terms (self-collisions): truncated integrals of every mode, contracted at once ----------
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double s1[3], s2[3];
+            const int n2d = cfg.n2d[i];
+            bool done = false;
+            if (i < N - 1 && cfg.quad[i]) {
+                const double nmd = pn[i], th = pa[i], k = pb[i];
+                const bool skip = (nmd == 0.0) || cell_empty || !live;
+                if (!__all_sync(0xffffffffu, skip)) {
+                    const int Mp = cfg.Mp[i];
+                    const double inv_th = 1.0 / th;
+                    const double log_th = log(th);
+                    const double gk = (cfg.kind[i] == CLOUDY_GAMMA) ? tgamma(k) : 1.0;
+                    const double a_top = k + (double)(Mp - 1);
+                    // own series degree / continued-fraction depth; loop bounds are the warp maxima
+                    const double X = cfg.thr[i] * inv_th;
+                    const double zmax = fmin(X, a_top + (double)kSeriesMargin);
+                    const int zi = (zmax >= 0.0) ? (int)fmin(zmax, (double)(kSeriesTabLen - 1)) : 0;
+                    const int deg = skip ? 1 : sh.deg[zi];
+                    const int deg_w = __reduce_max_sync(0xffffffffu, deg);
+                    const int ai = (int)fmin(fmax(a_top, 0.0), 17.0);
+                    const int cfd = sh.cfd[ai];
+                    const int cfd_w = __reduce_max_sync(0xffffffffu, cfd);
+                    {   // c_n = 1/(a)_{n+1}: one division, then c_{n-1} = c_n (a+n)
+                        double prod = 1.0;
+                        for (int nn = 0; nn <= deg; ++nn) prod *= (a_top + (double)nn);
+                        double cc = 1.0 / prod;
+                        for (int nn = deg; nn >= 0; --nn) {
+                            myCt[nn * TPP_THREADS] = cc;
+                            cc *= (a_top + (double)nn);
+                        }
+                        for (int nn = deg + 1; nn <= deg_w; ++nn) myCt[nn * TPP_THREADS] = 0.0;
+                    }
+                    const double pre0 = nmd * nmd / (gk * gk);
+                    const double* tb = sTab + cfg.tab_off[i];
+                    const int nb = cfg.n_bins[i];
+                    auto finish = [&](auto mp_tag) {
+                        constexpr int MP = decltype(mp_tag)::value;
+                        constexpr int T = MP * (MP + 1) / 2;
+                        double ia[MP];
+                        double gam_top = gk;
+#pragma unroll
+                        for (int pp = 0; pp < MP - 1; ++pp) {
+                            ia[pp] = 1.0 / (k + (double)pp);
+                            gam_top *= (k + (double)pp);  // Γ(k+MP-1)
+                        }
+                        ia[MP - 1] = 0.0;
+                        double F[T];
+                        tpp_nodes<MP>(F, tb, nb, k, inv_th, log_th, gam_top, ia, myCtc, deg_w, cfd_w, cfd, a_top);
+                        // F = 0 | min(Mom*Mom, H), H = n^2 θ^{p2}/Γ(k)^2 * sum — Coalescence.jl:212-227
+                        double thp[MP];
+                        thp[0] = pre0;
+#pragma unroll
+                        for (int pp = 1; pp < MP; ++pp) thp[pp] = thp[pp - 1] * th;
+#pragma unroll
+                        for (int p1 = 0; p1 < MP; ++p1)
+#pragma unroll
+                            for (int p2 = p1; p2 < MP; ++p2) {
+                                const int t = tri_ct(p1, p2, MP);
+                                const double mm = mom[i][p1] * mom[i][p2];
+                                const double H = thp[p2] * F[t];
+                                F[t] = (mm < kEps) ? 0.0 : jl_min(mm, H);
+                            }
+                        tpp_s_terms<P>(cfg, i, mom[i], [&](int x, int y) -> double {
+                            if (x >= MP || y >= MP) return 0.0;  // beyond N_2d_ints (Coalescence.jl:213)
+                            return (x <= y) ? F[tri_ct(x < MP ? x : 0, y < MP ? y : 0, MP)] : F[tri_ct(y < MP ? y : 0, x < MP ? x : 0, MP)];
+                        }, s1, s2);
+                    };
+                    if (Mp == M) finish(std::integral_constant<int, M>{});
+                    else finish(std::integral_constant<int, M - 1>{});
+                    done = true;
+                }
+            }
+            if (!done) {
+                const bool mono = (i < N - 1) && cfg.mono_thr[i];
+                const bool quad_skipped = (i < N - 1) && cfg.quad[i];  // whole warp empty: F = 0
+                const double th = pa[i], nn = pn[i];
+                const bool below = th < cfg.thr[i] / 2;
+                tpp_s_terms<P>(cfg, i, mom[i], [&](int x, int y) -> double {
+                    const double mm = mom[i][x] * mom[i][y];
+                    if (mm < kEps || x >= n2d || y >= n2d || quad_skipped) return 0.0;
+                    if (mono) {  // ParticleDistributions.jl:557-564
+                        double h = 0.0;
+                        if (below) {
+                            h = nn * nn;
+                            for (int e = 0; e < x + y; ++e) h *= th;
+                        }
+                        return jl_min(mm, h);
+                    }
+                    return mm;  // last mode or infinite threshold
+                }, s1, s2);
+            }
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                res[i][m] += s1[m];
+                if (i + 1 < N) res[i + 1][m] += s2[m];
+            }
+        }
+
+        // ---- Q and R (collisions between modes) — Coalescence.jl:260-351 -----------------------------
+        // U_jk[c][b] = sum_a c^{jk}_ab Mom_j[a+c];  R_jk(m) = sum_b Mom_k[b+m] U[0][b];
+        // Q_jk(m) = sum_c C(m,c) sum_b Mom_k[b+m-c] U[c][b]  (j < k)
+        double sumQ[N][3], sumR[N][3];
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+#pragma unroll
+            for (int m = 0; m < 3; ++m) { sumQ[k][m] = 0.0; sumR[k][m] = 0.0; }
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                double U[3][P];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int b = 0; b < P; ++b) {
+                        double u = 0.0;
+                        if (c == 0 || j < k) {
+#pragma unroll
+                            for (int a = 0; a < P; ++a) u = fma(cfg.c[j][k][a][b], mom[j][a + c], u);
+                        }
+                        U[c][b] = u;
+                    }
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    double r = 0.0;
+#pragma unroll
+                    for (int b = 0; b < P; ++b) r = fma(mom[k][b + m], U[0][b], r);
+                    sumR[k][m] += r;
+                    if (j < k) {
+                        double q = 0.0;
+#pragma unroll
+                        for (int c = 0; c <= m; ++c) {
+                            double qc = 0.0;
+#pragma unroll
+                            for (int b = 0; b < P; ++b) qc = fma(mom[k][b + m - c], U[c][b], qc);
+                            q += ((m == 2 && c == 1) ? 2.0 : 1.0) * qc;
+                        }
+                        sumQ[k][m] += q;
+                    }
+                }
+            }
+        }
+
+        // ---- assemble, combine with the stage update, store ---------------------------------------------
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const int s0 = cfg.slot0[k], np = cfg.nprog[k];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                if (m < np && live) {
+                    const int s = s0 + m;
+                    // sum(Q[:,k]) - sum(R[:,k]) + S[1,k] (+ S[2,k-1]) — Coalescence.jl:140-149 (res holds S1 + S2)
+                    double f = sumQ[k][m] - sumR[k][m] + res[k][m];
+                    if (!args.params_in) f *= cfg.norm[s];
+                    if (RAIN) {
+                        if (cell_empty) f = 0.0;
+                        const double fl = args.flux[s * args.s_flux + p];
+                        const double fl_up = ((p + 1) % cfg.nz == 0) ? 0.0 : args.flux[s * args.s_flux + p + 1];  // zero flux at the top
+                        f = f + (-(fl_up - fl) / cfg.dz);  // rainshaft_helpers.jl:83-87
+                    }
+                    double o;
+                    if (args.tend_only) {
+                        o = f;
+                    } else {
+                        double acc2 = args.ci * raw[k][m];
+                        if (args.u_n != nullptr) {
+                            double un = args.u_n[s * args.s_n + p];
+                            if (RAIN) un = (un < 0.0) ? 0.0 : un;
+                            acc2 = args.cn * un + acc2;
+                        }
+                        o = (acc2 + args.cf * (args.dt * f)) / args.div;
+                        if (RAIN) o = (o < 0.0) ? 0.0 : o;
+                    }
+                    args.out[s * args.s_out + p] = o;
+                }
+            }
+        }
+    }
+}
+
+typedef void (*tpp_fn)(const DevConfig, const KArgs);
+// returns nullptr when (N, P) has no thread-per-parcel instance (the generic lane-cooperative kernel is used)
+tpp_fn tpp_lookup(int N, int P, int model);
+
+}  // namespace cloudy

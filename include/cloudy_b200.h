@@ -96,7 +96,8 @@ int cloudy_sync(cloudy_ctx* ctx);
 const char* cloudy_last_error(void);
 /* number of CUDA kernels this context has launched so far (bench.py's gpu_launches) */
 int cloudy_launch_count(cloudy_ctx* ctx, int64_t* out);
-/* execution-shape knob: lanes cooperating on one parcel's quadrature nodes (1,2,4,8,16,32; 0 = default) */
+/* execution-shape knob: 0 = auto (thread-per-parcel kernel when the (n_modes, P) shape has an instance, else 8 lanes),
+ * 1 = thread per parcel, 4/8/16/32 = that many lanes cooperating on one parcel's quadrature nodes */
 int cloudy_set_lanes(cloudy_ctx* ctx, int lanes);
 
 /* ---- device state ---------------------------------------------------------------------------- */

@@ -18,7 +18,7 @@ def cb():
     return cloudy_b200
 
 
-def _check_box(cb, par, state, n_check, lanes=(8,)):
+def _check_box(cb, par, state, n_check, lanes=(0,)):
     opar = oracle_params(par)
     model = cb.CoalescenceModel(par)
     ref = np.zeros((n_check, state.shape[1]))
@@ -43,7 +43,7 @@ def test_c1_smoluchowski(cb):
 def test_c2_gamma_exp(cb):
     from cloudy_b200 import workloads as W
     par, state = W.c2_gamma_exp(n_parcels=3000)
-    _check_box(cb, par, state, 400, lanes=(4, 8, 16, 32))
+    _check_box(cb, par, state, 400, lanes=(1, 4, 8, 16, 32))
 
 
 def test_c2_gamma_gamma(cb):
@@ -59,13 +59,13 @@ def test_mono_gamma_and_long_kernel(cb):
     from cloudy_b200 import workloads as W
     for gen in (W.mono_gamma, W.long_kernel_two_modes):
         par, state = gen(n_parcels=300)
-        _check_box(cb, par, state, 120, lanes=(4, 8))
+        _check_box(cb, par, state, 120, lanes=(1, 4, 8))
 
 
 def test_c4_three_gamma_modes_order4(cb):
     from cloudy_b200 import workloads as W
     par, state = W.c4_three_modes(n_parcels=1000)
-    _check_box(cb, par, state, 60, lanes=(4, 8, 32))
+    _check_box(cb, par, state, 60, lanes=(1, 4, 8, 32))
 
 
 def test_ragged_and_empty_batches(cb):
@@ -74,9 +74,13 @@ def test_ragged_and_empty_batches(cb):
     par, state = W.c2_gamma_exp(n_parcels=67)
     full = _check_box(cb, par, state, 67)
     model = cb.CoalescenceModel(par)
-    for n in (1, 31, 33):
-        got = model.coal_tendency_host(state[:n])
-        assert np.array_equal(got, full[:n])  # a parcel's result does not depend on its neighbours: bit-identical
+    for lanes in (1, 8):
+        model.ctx.set_lanes(lanes)
+        full = model.coal_tendency_host(state)
+        for n in (1, 31, 33):
+            got = model.coal_tendency_host(state[:n])
+            assert np.array_equal(got, full[:n])  # a parcel's result does not depend on its neighbours: bit-identical
+    model.ctx.set_lanes(0)
     assert model.coal_tendency_host(np.zeros((0, 5))).shape == (0, 5)
 
 
@@ -98,7 +102,7 @@ def test_all_empty_and_extreme_parcels(cb):
         [100, 2.5, 0.07, 1, 1],
     ]
     state = np.array(rows, dtype=np.float64) * nf
-    _check_box(cb, par, state, len(rows), lanes=(4, 8, 16, 32))
+    _check_box(cb, par, state, len(rows), lanes=(1, 4, 8, 16, 32))
 
 
 def test_full_size_properties(cb):
