@@ -272,7 +272,7 @@ def run_b200(args):
             "dtype": "f64", "data": "synthetic", "config": config_dict(args, world),
             "pair_evals_per_s": value * 4,  # parcel-mode-pair evals/s = value x N^2
             "roofline": {
-                "bound": "fp64", "kernel": "rhs_kernel<4,LANES,BOX>", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "bound": "fp64", "kernel": "tpp_kernel<2,2,BOX>", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp64_peak if fp64_peak else None,
                 "peak_source": "DFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); nominal 37.2",
                 "flop_per_eval": FLOP_PER_EVAL, "kernel_ms": k_ms,

@@ -80,7 +80,7 @@ __device__ __forceinline__ int tri_index(int p1, int p2, int Mcols) {  // p1 <= 
 template <int MPMAX, int LANES, int NPL>
 __device__ __forceinline__ void node_integrals(double (&acc)[MPMAX * (MPMAX + 1) / 2], const double* __restrict__ tb, int nb, int M,
                                                int Mp, double k, double inv_th, double log_th, double gam_top,
-                                               const double* __restrict__ gtab, int deg_w, int cfd_w, int cfd, int lane) {
+                                               const double* __restrict__ gtab, int deg_w, int cfd_w, int cfd, double ser_lim, int lane) {
     constexpr int T = MPMAX * (MPMAX + 1) / 2;
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.0;
@@ -90,7 +90,6 @@ __device__ __forceinline__ void node_integrals(double (&acc)[MPMAX * (MPMAX + 1)
     const double* LZ = tb + 3 * nb;
     const double* W = tb + 4 * nb;
     const double a_top = k + (double)(Mp - 1);
-    const double ser_lim = a_top + (double)kSeriesMargin;
     const int batches = (nb + LANES * NPL - 1) / (LANES * NPL);
     for (int bt = 0; bt < batches; ++bt) {
         // NPL nodes per lane in flight: their Horner chains share every coefficient load and hide DFMA latency
@@ -365,13 +364,13 @@ __global__ void __launch_bounds__(Shape<LANES>::kThreads) rhs_kernel(const __gri
                     double* gtab = my + L.tab;
                     // series degree needed by this group: largest z is below X = x_th/θ and below the series limit
                     const double X = cfg.thr[md] * inv_th;
-                    double zmax = fmin(X, a_top + (double)kSeriesMargin);
-                    int zi = (zmax >= 0.0) ? (int)fmin(zmax, (double)(kSeriesTabLen - 1)) : 0;
+                    const int ai = series_a_bin(a_top);
+                    const double ser_lim = kSeriesLimit[ai];
+                    const int zi = series_z_bin(fmin(X, ser_lim - 0.5));
                     // a parcel's result must not depend on which parcels share its warp: the coefficient table is
                     // built from the group's OWN degree (zero above it), only the loop bounds are warp maxima
-                    const int deg = skip ? 1 : kSeriesDeg[zi];
+                    const int deg = skip ? 1 : max((int)kSeriesDeg2[zi][ai], 1);
                     const int deg_w = __reduce_max_sync(0xffffffffu, deg);
-                    int ai = (int)fmin(fmax(a_top, 0.0), 17.0);
                     const int cfd = kCfDepth[ai];
                     const int cfd_w = __reduce_max_sync(0xffffffffu, cfd);
                     // series coefficients c_n = 1/(a)_{n+1}, n = 0..deg, chunked over the lanes:
@@ -409,7 +408,7 @@ __global__ void __launch_bounds__(Shape<LANES>::kThreads) rhs_kernel(const __gri
                     for (int p = 0; p < Mp - 1; ++p) gam_top *= (k + (double)p);  // Γ(k+Mp-1)
                     double acc[T];
                     node_integrals<(MPMAX > 0 ? MPMAX : 1), LANES, NodesPerLane<LANES>::value>(acc, sTab + cfg.tab_off[md], cfg.n_bins[md], M, Mp, k, inv_th, log_th,
-                                                                  gam_top, gtab, deg_w, cfd_w, cfd, lane);
+                                                                  gam_top, gtab, deg_w, cfd_w, cfd, ser_lim, lane);
                     // F = 0 | min(Mom*Mom, H) — Coalescence.jl:212-227; H = n²θ^{p2}/Γ(k)² * Σ
                     const double* mom = my + L.mom + md * M;
                     const double pre0 = n_md * n_md * par[PAR_IGK2];

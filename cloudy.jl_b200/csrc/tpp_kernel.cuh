@@ -26,12 +26,17 @@ __host__ __device__ constexpr int tri_ct(int p1, int p2, int MP) { return p1 * M
 
 // ------------------------------------------------------------------------------------------------
 // node loop for one mode of one parcel: acc[t(p1,p2)] = sum_j W[p1][j] g_j gamma(k+p2, z_j)
+//   g_j = (x_j/θ)^k e^{-x_j/θ},  z_j = (x_th - x_j)/θ,  E_j = z_j^k e^{-z_j}
+// Series regime: gamma(k+p, z) = E h_p with h_top = z^{MP-1} S(z), h_p = (h_{p+1} + z^p)/(k+p), and
+//   g_j E_j = exp(k (ln x_j + ln(x_th - x_j) - 2 ln θ) - x_th/θ)   — ONE exponential per node.
+// Continued-fraction regime (z beyond the series limit): gamma(k+p, z) = Γ(a_top) A_p + E h_p with
+//   h_top = -z^{MP-1} Q/P, A_top = 1, A_p = A_{p+1}/(k+p); needs g_j on its own (a second exponential).
 // ------------------------------------------------------------------------------------------------
 template <int MP>
 __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], const double* __restrict__ tb, const int nb, const double k,
-                                          const double inv_th, const double log_th, const double gam_top, const double (&ia)[MP],
-                                          const double* __restrict__ myCt, const int deg_w, const int cfd_w, const int cfd,
-                                          const double a_top) {
+                                          const double inv_th, const double log_th, const double X, const double gam_top,
+                                          const double (&ia)[MP], const double* __restrict__ myCt, const int deg_w, const int cfd_w,
+                                          const int cfd, const double a_top, const double ser_lim) {
     constexpr int T = MP * (MP + 1) / 2;
     constexpr int NPL = TPP_NPL;
 #pragma unroll
@@ -41,9 +46,13 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
     const double* TMX = tb + 2 * nb;
     const double* LZ = tb + 3 * nb;
     const double* W = tb + 4 * nb;
-    const double ser_lim = a_top + (double)kSeriesMargin;
+    const double e0 = fma(-2.0 * k, log_th, -X);  // exponent offset of g*E
+    double A[MP];                                  // Γ(a_top) A_p
+    A[MP - 1] = gam_top;
+#pragma unroll
+    for (int p = MP - 2; p >= 0; --p) A[p] = A[p + 1] * ia[p];
     for (int j0 = 0; j0 < nb; j0 += NPL) {
-        double z[NPL], gtop[NPL];
+        double z[NPL], h[NPL];
         bool any_ser = false, any_cf = false;
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
@@ -51,88 +60,91 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
             z[i] = TMX[j] * inv_th;  // (x_th - x_j)/θ
             any_ser = any_ser || (z[i] < ser_lim);
             any_cf = any_cf || !(z[i] < ser_lim);
-            gtop[i] = 0.0;
+            h[i] = 0.0;
         }
         if (__any_sync(0xffffffffu, any_ser)) {
-            // series: gamma(a,z) = z^a e^-z * sum_n c_n z^n, Horner from the warp's largest degree (own table is
-            // zero above the parcel's own degree, so the result does not depend on the neighbours)
-            double s[NPL];
+            // Horner from the warp's largest degree; the own table is zero above the parcel's own degree, so the
+            // result does not depend on the neighbours
             const double c_top = myCt[deg_w * TPP_THREADS];
 #pragma unroll
-            for (int i = 0; i < NPL; ++i) s[i] = c_top;
+            for (int i = 0; i < NPL; ++i) h[i] = c_top;
             int n = deg_w - 1;
             for (; n >= 3; n -= 4) {
                 const double c0 = myCt[n * TPP_THREADS], c1 = myCt[(n - 1) * TPP_THREADS], c2 = myCt[(n - 2) * TPP_THREADS],
                              c3 = myCt[(n - 3) * TPP_THREADS];
 #pragma unroll
-                for (int i = 0; i < NPL; ++i) s[i] = fma(s[i], z[i], c0);
+                for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], z[i], c0);
 #pragma unroll
-                for (int i = 0; i < NPL; ++i) s[i] = fma(s[i], z[i], c1);
+                for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], z[i], c1);
 #pragma unroll
-                for (int i = 0; i < NPL; ++i) s[i] = fma(s[i], z[i], c2);
+                for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], z[i], c2);
 #pragma unroll
-                for (int i = 0; i < NPL; ++i) s[i] = fma(s[i], z[i], c3);
+                for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], z[i], c3);
             }
             for (; n >= 0; --n) {
                 const double c0 = myCt[n * TPP_THREADS];
 #pragma unroll
-                for (int i = 0; i < NPL; ++i) s[i] = fma(s[i], z[i], c0);
+                for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], z[i], c0);
             }
-#pragma unroll
-            for (int i = 0; i < NPL; ++i) gtop[i] = s[i];
         }
-        if (__any_sync(0xffffffffu, any_cf)) {
-            // Legendre continued fraction of Gamma(a,z)/(z^a e^-z), forward recurrence, fixed depth.  Beyond the
-            // parcel's own depth the step degenerates to P <- 1*P + 0, which is exact.
-            double Pm[NPL], Pc[NPL], Qm[NPL], Qc[NPL], b[NPL];
+        const bool warp_cf = __any_sync(0xffffffffu, any_cf);
+        if (warp_cf) {
+            // Legendre continued fraction of Gamma(a,z)/(z^a e^-z), forward recurrence, fixed depth, one node at a time
+            // (rare regime: keeps the register footprint of the common path small).  Beyond the parcel's own depth the
+            // step degenerates to P <- 1*P + 0, which is exact.
 #pragma unroll
             for (int i = 0; i < NPL; ++i) {
-                const double zc = fmin(z[i], 256.0);  // beyond this the upper function is < 1e-80 of Gamma(a)
-                b[i] = zc + 1.0 - a_top;
-                Pm[i] = 1.0; Pc[i] = b[i]; Qm[i] = 0.0; Qc[i] = 1.0;
-            }
-            double fn = 0.0;
-            for (int n = 1; n <= cfd_w; ++n) {
-                fn += 1.0;
-                const bool on = n <= cfd;
-                const double an = on ? fn * (a_top - fn) : 0.0;  // -n(n-a)
-#pragma unroll
-                for (int i = 0; i < NPL; ++i) {
-                    b[i] += 2.0;
-                    const double bb = on ? b[i] : 1.0;
-                    const double Pn = fma(bb, Pc[i], an * Pm[i]);
-                    const double Qn = fma(bb, Qc[i], an * Qm[i]);
-                    Pm[i] = Pc[i]; Pc[i] = Pn; Qm[i] = Qc[i]; Qc[i] = Qn;
+                const bool cf_i = !(z[i] < ser_lim);
+                if (__any_sync(0xffffffffu, cf_i)) {
+                    const double zc = fmin(z[i], 256.0);  // beyond this the upper function is < 1e-80 of Gamma(a)
+                    double b = zc + 1.0 - a_top;
+                    double Pm = 1.0, Pc = b, Qm = 0.0, Qc = 1.0, fn = 0.0;
+                    for (int n = 1; n <= cfd_w; ++n) {
+                        fn += 1.0;
+                        b += 2.0;
+                        const bool on = n <= cfd;
+                        const double an = on ? fn * (a_top - fn) : 0.0;  // -n(n-a)
+                        const double bb = on ? b : 1.0;
+                        const double Pn = fma(bb, Pc, an * Pm);
+                        const double Qn = fma(bb, Qc, an * Qm);
+                        Pm = Pc; Pc = Pn; Qm = Qc; Qc = Qn;
+                    }
+                    if (cf_i) h[i] = -(Qc / Pc);
                 }
             }
-#pragma unroll
-            for (int i = 0; i < NPL; ++i)
-                if (!(z[i] < ser_lim)) gtop[i] = -(Qc[i] / Pc[i]);
         }
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
             const int jraw = j0 + i;
             const int j = min(jraw, nb - 1);
-            const double u = XJ[j] * inv_th;
-            const double g = exp(fma(k, ELL[j] - log_th, -u));    // (x_j/θ)^k e^{-x_j/θ}
-            const double E = exp(fma(k, LZ[j] - log_th, -z[i]));  // z^k e^{-z}
+            double gE = exp(fma(k, ELL[j] + LZ[j], e0));  // g_j * E_j
+            gE = (jraw < nb) ? gE : 0.0;
             double zp[MP];
             zp[0] = 1.0;
 #pragma unroll
             for (int p = 1; p < MP; ++p) zp[p] = zp[p - 1] * z[i];
-            const double Etop = E * zp[MP - 1];
-            double gam[MP];
-            gam[MP - 1] = (z[i] < ser_lim) ? Etop * gtop[i] : fma(Etop, gtop[i], gam_top);
+            double v[MP];
+            double hp = zp[MP - 1] * h[i];
+            v[MP - 1] = gE * hp;
 #pragma unroll
-            for (int p = MP - 2; p >= 0; --p) gam[p] = (gam[p + 1] + E * zp[p]) * ia[p];  // downward recurrence
-            const double gv = (jraw < nb) ? g : 0.0;
+            for (int p = MP - 2; p >= 0; --p) {
+                hp = (hp + zp[p]) * ia[p];  // downward recurrence
+                v[p] = gE * hp;
+            }
+            if (warp_cf) {
+                const bool cf_i = !(z[i] < ser_lim);
+                double g = exp(fma(k, ELL[j] - log_th, -(XJ[j] * inv_th)));  // (x_j/θ)^k e^{-x_j/θ}
+                g = (cf_i && jraw < nb) ? g : 0.0;
+#pragma unroll
+                for (int p = 0; p < MP; ++p) v[p] = fma(g, A[p], v[p]);
+            }
             int t = 0;
 #pragma unroll
             for (int p1 = 0; p1 < MP; ++p1) {
-                const double wg = W[p1 * nb + j] * gv;
+                const double w = W[p1 * nb + j];
 #pragma unroll
                 for (int p2 = p1; p2 < MP; ++p2) {
-                    acc[t] = fma(wg, gam[p2], acc[t]);
+                    acc[t] = fma(w, v[p2], acc[t]);
                     ++t;
                 }
             }
@@ -172,8 +184,9 @@ __device__ __forceinline__ void tpp_s_terms(const DevConfig& cfg, const int k, c
 }
 
 struct TppShared {
-    int deg[kSeriesTabLen];
-    int cfd[18];
+    unsigned char deg[kSerZ][kSerA];
+    double serlim[kSerA];
+    int cfd[kSerA];
 };
 
 template <int N, int P, int MODEL>
@@ -186,8 +199,8 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
     double* sCt = smem + ((cfg.tab_total + 1) & ~1);
     const int tid = threadIdx.x;
     for (int i = tid; i < cfg.tab_total; i += TPP_THREADS) sTab[i] = cfg.tab[i];
-    if (tid < kSeriesTabLen) sh.deg[tid] = kSeriesDeg[tid];
-    if (tid < 18) sh.cfd[tid] = kCfDepth[tid];
+    for (int i = tid; i < kSerZ * kSerA; i += TPP_THREADS) sh.deg[i / kSerA][i % kSerA] = kSeriesDeg2[i / kSerA][i % kSerA];
+    if (tid < kSerA) { sh.cfd[tid] = kCfDepth[tid]; sh.serlim[tid] = kSeriesLimit[tid]; }
     __syncthreads();
     const double* myCtc = sCt + tid;
     double* myCt = sCt + tid;
@@ -266,11 +279,11 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
                     const double a_top = k + (double)(Mp - 1);
                     // own series degree / continued-fraction depth; loop bounds are the warp maxima
                     const double X = cfg.thr[i] * inv_th;
-                    const double zmax = fmin(X, a_top + (double)kSeriesMargin);
-                    const int zi = (zmax >= 0.0) ? (int)fmin(zmax, (double)(kSeriesTabLen - 1)) : 0;
-                    const int deg = skip ? 1 : sh.deg[zi];
+                    const int ai = series_a_bin(a_top);
+                    const double ser_lim = sh.serlim[ai];
+                    const int zi = series_z_bin(fmin(X, ser_lim - 0.5));
+                    const int deg = skip ? 1 : max((int)sh.deg[zi][ai], 1);
                     const int deg_w = __reduce_max_sync(0xffffffffu, deg);
-                    const int ai = (int)fmin(fmax(a_top, 0.0), 17.0);
                     const int cfd = sh.cfd[ai];
                     const int cfd_w = __reduce_max_sync(0xffffffffu, cfd);
                     {   // c_n = 1/(a)_{n+1}: one division, then c_{n-1} = c_n (a+n)
@@ -298,7 +311,7 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
                         }
                         ia[MP - 1] = 0.0;
                         double F[T];
-                        tpp_nodes<MP>(F, tb, nb, k, inv_th, log_th, gam_top, ia, myCtc, deg_w, cfd_w, cfd, a_top);
+                        tpp_nodes<MP>(F, tb, nb, k, inv_th, log_th, X, gam_top, ia, myCtc, deg_w, cfd_w, cfd, a_top, ser_lim);
                         // F = 0 | min(Mom*Mom, H), H = n^2 θ^{p2}/Γ(k)^2 * sum — Coalescence.jl:212-227
                         double thp[MP];
                         thp[0] = pre0;
