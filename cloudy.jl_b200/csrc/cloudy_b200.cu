@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(Shape<LANES>::kThreads) rhs_kernel(const __gri
             bool in_range = p < args.n;
             if (RAIN && g == G) in_range = in_range && (p % cfg.nz != 0);  // halo must be in the same column
             if (in_range) {
-                v = args.u_in[s * args.s_in + p];
+                v = args.u_in[s * args.s_in + p * args.ps_in];
                 if (RAIN) v = (v < 0.0) ? 0.0 : v;  // rainshaft_helpers.jl:52
                 if (args.u_n != nullptr && g < G) {
                     vn = args.u_n[s * args.s_n + p];
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(Shape<LANES>::kThreads) rhs_kernel(const __gri
                 o = (acc2 + args.cf * (args.dt * f)) / args.div;
                 if (RAIN) o = (o < 0.0) ? 0.0 : o;  // clipped by the next RHS evaluation (rainshaft_helpers.jl:52)
             }
-            args.out[s * args.s_out + p] = o;
+            args.out[s * args.s_out + p * args.ps_out] = o;
         }
     }
 }
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevCo
             const int s0 = cfg.slot0[i], np = cfg.nprog[i], kind = cfg.kind[i];
             double mn[3] = {0.0, 0.0, 0.0};
             for (int q = 0; q < np; ++q) {
-                double v = args.u_in[(s0 + q) * args.s_in + p];
+                double v = args.u_in[(s0 + q) * args.s_in + p * args.ps_in];
                 v = (v < 0.0) ? 0.0 : v;  // rainshaft_helpers.jl:52
                 mn[q] = v / cfg.norm[s0 + q];
             }
@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevCo
                     else mq *= mp.a;
                 }
             }
-            for (int q = 0; q < np; ++q) args.out[(s0 + q) * args.s_out + p] = fl[q] * cfg.norm[s0 + q];
+            for (int q = 0; q < np; ++q) args.out[(s0 + q) * args.s_out + p * args.ps_out] = fl[q] * cfg.norm[s0 + q];
         }
     }
 }
@@ -773,6 +773,13 @@ struct cloudy_ctx {
     cloudy_state* tmp[3];  // stepper / host-path work buffers
     cloudy_state* flux;    // rainshaft: per-cell sedimentation flux for the thread-per-parcel kernel
     double* d_stage_aos;   // staging for upload/download
+    // host-buffer pipeline (cloudy_coal_tendency_host): chunked H2D / kernel / D2H on three streams
+    cudaStream_t s_h2d, s_d2h;
+    cudaEvent_t ev_in[3], ev_k[3], ev_out[3];
+    double* d_pipe_in[3];
+    double* d_pipe_out[3];
+    long long pipe_chunk;
+    bool pipe_ready;
     long long stage_cap;
 };
 
@@ -931,6 +938,17 @@ int cloudy_ctx_destroy(cloudy_ctx* ctx) {
     cudaFree(ctx->d_partial);
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_stage_aos);
+    if (ctx->pipe_ready) {
+        for (int i = 0; i < 3; ++i) {
+            cudaFree(ctx->d_pipe_in[i]);
+            cudaFree(ctx->d_pipe_out[i]);
+            cudaEventDestroy(ctx->ev_in[i]);
+            cudaEventDestroy(ctx->ev_k[i]);
+            cudaEventDestroy(ctx->ev_out[i]);
+        }
+        cudaStreamDestroy(ctx->s_h2d);
+        cudaStreamDestroy(ctx->s_d2h);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return CLOUDY_OK;
@@ -1168,6 +1186,7 @@ static KArgs base_args(cloudy_ctx* ctx, const cloudy_state* in, cloudy_state* ou
     a.u_in = in->d; a.s_in = in->stride;
     a.out = out->d; a.s_out = out->stride;
     a.n = in->n;
+    a.ps_in = 1; a.ps_out = 1;
     a.cn = 0; a.ci = 1; a.cf = 1; a.dt = 1; a.div = 1;
     a.err_count = ctx->d_err;
     return a;
@@ -1247,6 +1266,7 @@ int cloudy_ssprk33_steps(cloudy_ctx* ctx, cloudy_state* u, double dt, int32_t n_
         memset(&a, 0, sizeof(a));
         a.n = u->n; a.dt = dt; a.err_count = ctx->d_err;
         a.s_in = a.s_n = a.s_out = st;
+        a.ps_in = a.ps_out = 1;
         // stage 1: tmp = u + dt f(u)
         a.u_in = cur; a.u_n = nullptr; a.out = t1; a.cn = 0; a.ci = 1; a.cf = 1; a.div = 1;
         if ((rc = launch_rhs(ctx, model, a))) return rc;
@@ -1285,16 +1305,83 @@ int cloudy_moment_sums(cloudy_ctx* ctx, const cloudy_state* u, double* host_out)
     return CLOUDY_OK;
 }
 
+static int ensure_pipe(cloudy_ctx* ctx, long long chunk) {
+    if (ctx->pipe_ready && ctx->pipe_chunk >= chunk) return CLOUDY_OK;
+    if (!ctx->pipe_ready) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 3; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+        }
+        ctx->pipe_ready = true;
+    }
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 3; ++i) {
+        cudaFree(ctx->d_pipe_in[i]);
+        cudaFree(ctx->d_pipe_out[i]);
+        ctx->d_pipe_in[i] = ctx->d_pipe_out[i] = nullptr;
+    }
+    ctx->pipe_chunk = 0;
+    for (int i = 0; i < 3; ++i) {
+        CUDA_TRY(cudaMalloc(&ctx->d_pipe_in[i], sizeof(double) * chunk * MAXSLOT));
+        CUDA_TRY(cudaMalloc(&ctx->d_pipe_out[i], sizeof(double) * chunk * MAXSLOT));
+    }
+    ctx->pipe_chunk = chunk;
+    return CLOUDY_OK;
+}
+
+// Host moments in, host tendencies out.  The batch is cut into chunks that flow through a three-stage pipeline
+// (H2D copy | kernel | D2H copy) on three streams, so PCIe traffic in both directions overlaps the arithmetic.
+// The kernel reads and writes the host (array-of-structures) layout directly: no transpose pass.
 int cloudy_coal_tendency_host(cloudy_ctx* ctx, const double* host_m, double* host_dm, int64_t n_parcels) {
     if (!ctx || (!host_m && n_parcels) || (!host_dm && n_parcels)) return fail(CLOUDY_ERR_ARG, "NULL argument");
     if (!ctx->configured) return fail(CLOUDY_ERR_STATE, "cloudy_config_set has not been called");
+    if (n_parcels < 0) return fail(CLOUDY_ERR_ARG, "negative parcel count");
     if (n_parcels == 0) return CLOUDY_OK;
-    int rc;
-    if ((rc = ensure_tmp(ctx, 0, n_parcels))) return rc;
-    if ((rc = ensure_tmp(ctx, 1, n_parcels))) return rc;
-    if ((rc = cloudy_state_upload(ctx, ctx->tmp[0], host_m, n_parcels))) return rc;
-    if ((rc = cloudy_coal_tendency(ctx, ctx->tmp[0], ctx->tmp[1]))) return rc;
-    return cloudy_state_download(ctx, ctx->tmp[1], host_dm, n_parcels);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int ns = ctx->dev.nslots;
+    long long chunk = 131072;
+    if (n_parcels < chunk) chunk = n_parcels;
+    int rc = ensure_pipe(ctx, std::max<long long>(chunk, 1024));
+    if (rc) return rc;
+    const long long n_chunks = (n_parcels + chunk - 1) / chunk;
+    // the pipeline starts after everything already enqueued on the context's stream
+    CUDA_TRY(cudaEventRecord(ctx->ev_k[0], ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_k[0], 0));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[0], 0));
+    for (long long c = 0; c < n_chunks; ++c) {
+        const int b = (int)(c % 3);
+        const long long p0 = c * chunk;
+        const long long m = std::min<long long>(chunk, n_parcels - p0);
+        // buffer b is free once chunk c-3 has been copied back (input buffer: once its kernel has run)
+        if (c >= 3) {
+            CUDA_TRY(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_k[b], 0));
+            CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));
+        }
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_pipe_in[b], host_m + p0 * ns, sizeof(double) * m * ns, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CUDA_TRY(cudaEventRecord(ctx->ev_in[b], ctx->s_h2d));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
+        KArgs a;
+        memset(&a, 0, sizeof(a));
+        a.u_in = ctx->d_pipe_in[b]; a.s_in = 1; a.ps_in = ns;
+        a.out = ctx->d_pipe_out[b]; a.s_out = 1; a.ps_out = ns;
+        a.n = m;
+        a.cn = 0; a.ci = 1; a.cf = 1; a.dt = 1; a.div = 1;
+        a.tend_only = 1;
+        a.err_count = ctx->d_err;
+        if ((rc = launch_rhs(ctx, CLOUDY_MODEL_BOX, a))) return rc;
+        CUDA_TRY(cudaEventRecord(ctx->ev_k[b], ctx->stream));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_k[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(host_dm + p0 * ns, ctx->d_pipe_out[b], sizeof(double) * m * ns, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CUDA_TRY(cudaEventRecord(ctx->ev_out[b], ctx->s_d2h));
+    }
+    // later work on the context's stream is ordered after the last copy-back; the call itself is synchronous
+    CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[(n_chunks - 1) % 3], 0));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_d2h));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return CLOUDY_OK;
 }
 
 int cloudy_error_count(cloudy_ctx* ctx, int64_t* n_invalid) {

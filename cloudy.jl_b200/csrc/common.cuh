@@ -45,7 +45,8 @@ struct KArgs {
     double* out;          // tendency, flux or stage result
     double* clip_back;    // rainshaft tendency call: clipped state written back (nullptr otherwise)
     long long n;          // parcels / cells
-    long long s_in, s_n, s_out, s_clip;  // SoA strides (doubles)
+    long long s_in, s_n, s_out, s_clip;  // slot strides (doubles): SoA = ensemble stride, AoS = 1
+    long long ps_in, ps_out;             // parcel strides of u_in / out: SoA = 1, AoS (host layout) = n_slots
     double cn, ci, cf, dt, div;          // out = (cn*u_n + ci*u_in + cf*(dt*f))/div ; tend_only: out = f
     int tend_only;
     int flux_only;        // out = sedimentation flux (rainshaft_helpers.jl:77)

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
             for (int q = 0; q < 3; ++q) {
                 raw[i][q] = 0.0;
                 if (q < np) {
-                    double v = args.u_in[(s0 + q) * args.s_in + p];
+                    double v = args.u_in[(s0 + q) * args.s_in + p * args.ps_in];
                     if (RAIN) {
                         v = (v < 0.0) ? 0.0 : v;  // rainshaft_helpers.jl:52
                         if (args.clip_back != nullptr && live) args.clip_back[(s0 + q) * args.s_clip + p] = v;
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
                         o = (acc2 + args.cf * (args.dt * f)) / args.div;
                         if (RAIN) o = (o < 0.0) ? 0.0 : o;
                     }
-                    args.out[s * args.s_out + p] = o;
+                    args.out[s * args.s_out + p * args.ps_out] = o;
                 }
             }
         }
