@@ -67,6 +67,14 @@ def config_dict(args, world):
 # ---------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle's structure-faithful C/OpenMP restatement on the host cores
 # ---------------------------------------------------------------------------------------------------
+def host_threads():
+    """all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the scheduler instead)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_rate(par, state, seconds, threads):
     import cloudy_b200 as cb
     from oracle import c_oracle
@@ -87,7 +95,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import c_oracle
-    threads = c_oracle.max_threads()
+    threads = host_threads()
     sample = 2048 * threads
     par, state = workload(sample)
     import cloudy_b200 as cb
@@ -287,8 +295,7 @@ def run_b200(args):
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
-            from oracle import c_oracle
-            threads = c_oracle.max_threads()
+            threads = host_threads()
             rate, ns, dt = cpu_rate(par, state0, args.cpu_seconds, threads)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"first {ns} parcels of the same ensemble, {dt:.1f} s; C/OpenMP structure-faithful "

@@ -631,17 +631,6 @@ struct ScalarArgs {
     int* iout;
 };
 
-__device__ inline double simpson_weight(int j, int n_bins) {  // 1-based node j of ParticleDistributions.jl:698-710 (numerators /48)
-    const int e = n_bins + 1;
-    double w = 0.0;
-    if (j >= 5 && j <= n_bins - 3) w += 48.0;
-    if (j == 1 || j == e) w += 17.0;
-    if (j == 2 || j == e - 1) w += 59.0;
-    if (j == 3 || j == e - 2) w += 43.0;
-    if (j == 4 || j == e - 3) w += 49.0;
-    return w;
-}
-
 __global__ void scalar_kernel(const ScalarArgs a) {
     const int lane = threadIdx.x;
     if (a.op == 0) {
@@ -868,10 +857,11 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
 static int launch_rhs(cloudy_ctx* ctx, int model, const KArgs& args) {
     // lanes == 0: thread-per-parcel kernel when the (N, P) shape has an instance, else the lane-cooperative kernel (8 lanes);
     // lanes == 1: thread-per-parcel required; lanes in {4, 8, 16, 32}: lane-cooperative kernel
-    if (ctx->lanes <= 1) {
+    const bool need_tpp = ctx->dev.thr_style == CLOUDY_MOVING_THRESHOLD || ctx->dev.ln_thr[0] || ctx->dev.ln_thr[1] || ctx->dev.ln_thr[2];
+    if (ctx->lanes <= 1 || need_tpp) {
         tpp_fn fn = tpp_lookup(ctx->dev.N, ctx->dev.P, model == CLOUDY_MODEL_RAINSHAFT ? MODEL_RAINSHAFT : MODEL_BOX);
         if (fn) return launch_tpp(ctx, fn, model, args);
-        if (ctx->lanes == 1) return fail(CLOUDY_ERR_UNSUPPORTED, "no thread-per-parcel kernel instance for this (n_modes, P)");
+        if (ctx->lanes == 1 || need_tpp) return fail(CLOUDY_ERR_UNSUPPORTED, "no thread-per-parcel kernel instance for this (n_modes, P)");
     }
     const int lanes = ctx->lanes <= 1 ? 8 : ctx->lanes;
     KernelEntry ke = (model == CLOUDY_MODEL_RAINSHAFT) ? pick_lanes<MODEL_RAINSHAFT>(lanes, ctx->mpmax)
@@ -981,8 +971,11 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
     if (N < 1 || N > MAXN) return fail(CLOUDY_ERR_ARG, "n_modes must be 1..4");
     if (P < 1 || P > MAXP) return fail(CLOUDY_ERR_ARG, "P must be 1..5");
     if (!(cfg->norms[0] > 0) || !(cfg->norms[1] > 0)) return fail(CLOUDY_ERR_ARG, "norms must be positive!");
-    if (cfg->threshold_style != CLOUDY_FIXED_THRESHOLD)
-        return fail(CLOUDY_ERR_UNSUPPORTED, "MovingThreshold is not implemented yet (SURVEY §8(f) rank 1)");
+    const bool moving = cfg->threshold_style == CLOUDY_MOVING_THRESHOLD;
+    if (cfg->threshold_style != CLOUDY_FIXED_THRESHOLD && !moving) return fail(CLOUDY_ERR_ARG, "unknown threshold style");
+    if (moving && !tpp_lookup(N, P, MODEL_BOX))
+        return fail(CLOUDY_ERR_UNSUPPORTED, "MovingThreshold needs a thread-per-parcel kernel instance for this (n_modes, P)");
+    if (!(cfg->k_range[1] <= 11.0)) return fail(CLOUDY_ERR_UNSUPPORTED, "k_range upper bound above 11 is outside the incomplete-gamma tables");
     DevConfig d;
     memset((void*)&d, 0, sizeof(d));
     d.N = N; d.P = P; d.M = P + 2;
@@ -1013,16 +1006,37 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
     // grid tables
     std::vector<double> tab;
     int mpmax = 0;
+    bool any_ln = false;
     for (int i = 0; i < N; ++i) {
         d.n2d[i] = cfg->n_2d_ints[i];
         d.Mp[i] = std::min(d.M, d.n2d[i]);
         d.thr[i] = cfg->thresholds[i];
-        const bool finite_thr = (i < N - 1) && !std::isinf(cfg->thresholds[i]);
-        if (finite_thr && cfg->kind[i] == CLOUDY_LOGNORMAL)
-            return fail(CLOUDY_ERR_UNSUPPORTED, "Lognormal mode with a finite threshold is not implemented yet");
+        bool finite_thr = (i < N - 1) && !std::isinf(cfg->thresholds[i]);
+        if (moving) {
+            // thresholds are mass percentiles; compute_threshold exists for Exponential and Gamma only
+            // (ParticleDistributions.jl:747-761); percentile 1 gives an infinite threshold
+            const double pct = cfg->thresholds[i];
+            if (i < N - 1) {
+                if (cfg->kind[i] != CLOUDY_GAMMA && cfg->kind[i] != CLOUDY_EXPONENTIAL)
+                    return fail(CLOUDY_ERR_ARG, "MethodError: compute_threshold is defined for Exponential and Gamma distributions only");
+                if (!(pct >= 0.0 && pct <= 1.0)) return fail(CLOUDY_ERR_ARG, "percentile must be in [0, 1]");
+                finite_thr = pct < 1.0;
+            }
+        }
+        if (finite_thr && cfg->kind[i] == CLOUDY_LOGNORMAL && !tpp_lookup(N, P, MODEL_BOX))
+            return fail(CLOUDY_ERR_UNSUPPORTED, "Lognormal mode with a finite threshold needs a thread-per-parcel kernel instance");
+        d.ln_thr[i] = finite_thr && cfg->kind[i] == CLOUDY_LOGNORMAL;
         d.mono_thr[i] = finite_thr && cfg->kind[i] == CLOUDY_MONODISPERSE;
         d.quad[i] = finite_thr && (cfg->kind[i] == CLOUDY_GAMMA || cfg->kind[i] == CLOUDY_EXPONENTIAL);
-        if (d.quad[i]) {
+        if (d.quad[i] && moving) {
+            if (d.Mp[i] < 2) return fail(CLOUDY_ERR_ARG, "N_2d_ints too small");
+            mpmax = std::max(mpmax, d.Mp[i]);
+        }
+        if (d.ln_thr[i]) {
+            if (!(cfg->thresholds[i] > 0)) return fail(CLOUDY_ERR_ARG, "thresholds must be positive");
+            any_ln = true;
+        }
+        if (d.quad[i] && !moving) {
             const int nb = cfg->n_bins[i];
             if (!(cfg->thresholds[i] > 0)) return fail(CLOUDY_ERR_ARG, "thresholds must be positive");
             if (nb < 3) return fail(CLOUDY_ERR_ARG, "n_bins must be at least 3");
@@ -1055,6 +1069,33 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
             mpmax = std::max(mpmax, d.Mp[i]);
         }
     }
+    if (any_ln) {
+        // Gauss-Legendre rule on [-1, 1] (Newton iteration on the Legendre polynomial), nodes then weights
+        const int n = 128;
+        d.gl_off = (int)tab.size();
+        d.gl_n = n;
+        std::vector<double> xs(n), ws(n);
+        for (int i = 0; i < (n + 1) / 2; ++i) {
+            double x = cos(M_PI * (i + 0.75) / (n + 0.5)), pp = 0.0;
+            for (int it = 0; it < 100; ++it) {
+                double p1 = 1.0, p2 = 0.0;
+                for (int j = 0; j < n; ++j) {
+                    const double p3 = p2;
+                    p2 = p1;
+                    p1 = ((2.0 * j + 1.0) * x * p2 - j * p3) / (j + 1.0);
+                }
+                pp = n * (x * p1 - p2) / (x * x - 1.0);
+                const double dxn = p1 / pp;
+                x -= dxn;
+                if (fabs(dxn) < 1e-16) break;
+            }
+            xs[i] = -x; xs[n - 1 - i] = x;
+            ws[i] = ws[n - 1 - i] = 2.0 / ((1.0 - x * x) * pp * pp);
+        }
+        tab.insert(tab.end(), xs.begin(), xs.end());
+        tab.insert(tab.end(), ws.begin(), ws.end());
+    }
+    d.bins_per_log_unit = cfg->bins_per_log_unit > 0 ? cfg->bins_per_log_unit : 15;
     d.tab_total = (int)tab.size();
     cudaFree(ctx->d_tab);
     ctx->d_tab = nullptr;
@@ -1461,8 +1502,8 @@ int cloudy_moment_source_helper(cloudy_ctx* ctx, int32_t kind, const double* par
         *out = (params[1] < x_threshold / 2) ? v : 0.0;
         return CLOUDY_OK;
     }
-    if (kind != CLOUDY_EXPONENTIAL && kind != CLOUDY_GAMMA)
-        return fail(CLOUDY_ERR_UNSUPPORTED, "moment_source_helper: Lognormal is not implemented yet");
+    if (kind == CLOUDY_LOGNORMAL) return fail(CLOUDY_ERR_UNSUPPORTED, "moment_source_helper(Lognormal): use a configured model (batched path only)");
+    if (kind != CLOUDY_EXPONENTIAL && kind != CLOUDY_GAMMA) return fail(CLOUDY_ERR_ARG, "unknown distribution kind");
     if (!(x_threshold > 0)) return fail(CLOUDY_ERR_ARG, "x_threshold must be positive");
     ScalarArgs a;
     memset(&a, 0, sizeof(a));

@@ -27,6 +27,9 @@ struct DevConfig {
     int n2d[MAXN], Mp[MAXN];       // Mp = min(M, n2d): orders 0..Mp-1 carry truncated integrals
     int quad[MAXN];                // 1: Gamma/Exponential mode with finite threshold, not last → node loop
     int mono_thr[MAXN];            // 1: Monodisperse mode with finite threshold, not last → closed form
+    int ln_thr[MAXN];              // 1: Lognormal mode with finite threshold, not last → Gauss-Legendre quadrature
+    int gl_off, gl_n;              // Gauss-Legendre nodes/weights on [-1,1] inside `tab` (nodes then weights)
+    int bins_per_log_unit;         // MovingThreshold: per-parcel grid density (15 in the reference)
     int n_bins[MAXN], tab_off[MAXN];
     int tab_total;                 // doubles of grid tables to stage in shared memory
     int n_vel, nz;

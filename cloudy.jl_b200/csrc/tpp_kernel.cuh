@@ -25,6 +25,42 @@ constexpr int TPP_CT_ROWS = 64;  // series coefficients c_0..c_63
 __host__ __device__ constexpr int tri_ct(int p1, int p2, int MP) { return p1 * MP - (p1 * (p1 - 1)) / 2 + (p2 - p1); }
 
 // ------------------------------------------------------------------------------------------------
+// node grids of the reference's log-spaced Simpson rule (ParticleDistributions.jl:579-585, :698-710)
+// ------------------------------------------------------------------------------------------------
+struct TableGrid {  // FixedThreshold: one grid per mode, built on the host, broadcast from shared memory
+    const double* XJ; const double* ELL; const double* TMX; const double* LZ; const double* W;
+    int nb;
+    __device__ __forceinline__ TableGrid(const double* tb, int n) : XJ(tb), ELL(tb + n), TMX(tb + 2 * n), LZ(tb + 3 * n), W(tb + 4 * n), nb(n) {}
+    __device__ __forceinline__ int count() const { return nb; }
+    __device__ __forceinline__ double tmx(int j) const { return TMX[j]; }
+    __device__ __forceinline__ double log_sum(int j) const { return ELL[j] + LZ[j]; }  // ln x_j + ln(x_th - x_j)
+    __device__ __forceinline__ double ell(int j) const { return ELL[j]; }
+    __device__ __forceinline__ double x(int j) const { return XJ[j]; }
+    template <int MP>
+    __device__ __forceinline__ void weights(int j, double (&w)[MP]) const {
+#pragma unroll
+        for (int p = 0; p < MP; ++p) w[p] = W[p * nb + j];  // w_j dx x_j^p
+    }
+};
+
+struct MovingGrid {  // MovingThreshold: the grid follows the parcel's own threshold
+    double x_min, dx, T;
+    int nb;
+    __device__ __forceinline__ int count() const { return nb; }
+    __device__ __forceinline__ double ell(int j) const { return x_min + (double)j * dx; }  // logx(x_min, j+1, dx)
+    __device__ __forceinline__ double x(int j) const { return exp(ell(j)); }
+    __device__ __forceinline__ double tmx(int j) const { return T - x(j); }
+    __device__ __forceinline__ double log_sum(int j) const { return ell(j) + log(tmx(j)); }
+    template <int MP>
+    __device__ __forceinline__ void weights(int j, double (&w)[MP]) const {
+        const double xj = x(j);
+        w[0] = simpson_weight(j + 1, nb) * (dx / 48.0);
+#pragma unroll
+        for (int p = 1; p < MP; ++p) w[p] = w[p - 1] * xj;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
 // node loop for one mode of one parcel: acc[t(p1,p2)] = sum_j W[p1][j] g_j gamma(k+p2, z_j)
 //   g_j = (x_j/θ)^k e^{-x_j/θ},  z_j = (x_th - x_j)/θ,  E_j = z_j^k e^{-z_j}
 // Series regime: gamma(k+p, z) = E h_p with h_top = z^{MP-1} S(z), h_p = (h_{p+1} + z^p)/(k+p), and
@@ -32,8 +68,8 @@ __host__ __device__ constexpr int tri_ct(int p1, int p2, int MP) { return p1 * M
 // Continued-fraction regime (z beyond the series limit): gamma(k+p, z) = Γ(a_top) A_p + E h_p with
 //   h_top = -z^{MP-1} Q/P, A_top = 1, A_p = A_{p+1}/(k+p); needs g_j on its own (a second exponential).
 // ------------------------------------------------------------------------------------------------
-template <int MP>
-__device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], const double* __restrict__ tb, const int nb, const double k,
+template <int MP, typename Grid>
+__device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], const Grid grid, const double k,
                                           const double inv_th, const double log_th, const double X, const double gam_top,
                                           const double (&ia)[MP], const double* __restrict__ myCt, const int deg_w, const int cfd_w,
                                           const int cfd, const double a_top, const double ser_lim) {
@@ -41,23 +77,20 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
     constexpr int NPL = TPP_NPL;
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.0;
-    const double* XJ = tb;
-    const double* ELL = tb + nb;
-    const double* TMX = tb + 2 * nb;
-    const double* LZ = tb + 3 * nb;
-    const double* W = tb + 4 * nb;
+    const int nb = grid.count();                               // own node count
+    const int nb_w = __reduce_max_sync(0xffffffffu, nb);      // loop bound: the warp's largest grid
     const double e0 = fma(-2.0 * k, log_th, -X);  // exponent offset of g*E
     double A[MP];                                  // Γ(a_top) A_p
     A[MP - 1] = gam_top;
 #pragma unroll
     for (int p = MP - 2; p >= 0; --p) A[p] = A[p + 1] * ia[p];
-    for (int j0 = 0; j0 < nb; j0 += NPL) {
+    for (int j0 = 0; j0 < nb_w; j0 += NPL) {
         double z[NPL], h[NPL];
         bool any_ser = false, any_cf = false;
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
             const int j = min(j0 + i, nb - 1);
-            z[i] = TMX[j] * inv_th;  // (x_th - x_j)/θ
+            z[i] = grid.tmx(j) * inv_th;  // (x_th - x_j)/θ
             any_ser = any_ser || (z[i] < ser_lim);
             any_cf = any_cf || !(z[i] < ser_lim);
             h[i] = 0.0;
@@ -117,7 +150,7 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
         for (int i = 0; i < NPL; ++i) {
             const int jraw = j0 + i;
             const int j = min(jraw, nb - 1);
-            double gE = exp(fma(k, ELL[j] + LZ[j], e0));  // g_j * E_j
+            double gE = exp(fma(k, grid.log_sum(j), e0));  // g_j * E_j
             gE = (jraw < nb) ? gE : 0.0;
             double zp[MP];
             zp[0] = 1.0;
@@ -133,22 +166,65 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
             }
             if (warp_cf) {
                 const bool cf_i = !(z[i] < ser_lim);
-                double g = exp(fma(k, ELL[j] - log_th, -(XJ[j] * inv_th)));  // (x_j/θ)^k e^{-x_j/θ}
+                double g = exp(fma(k, grid.ell(j) - log_th, -(grid.x(j) * inv_th)));  // (x_j/θ)^k e^{-x_j/θ}
                 g = (cf_i && jraw < nb) ? g : 0.0;
 #pragma unroll
                 for (int p = 0; p < MP; ++p) v[p] = fma(g, A[p], v[p]);
             }
+            double w[MP];
+            grid.template weights<MP>(j, w);
             int t = 0;
 #pragma unroll
             for (int p1 = 0; p1 < MP; ++p1) {
-                const double w = W[p1 * nb + j];
 #pragma unroll
                 for (int p2 = p1; p2 < MP; ++p2) {
-                    acc[t] = fma(w, v[p2], acc[t]);
+                    acc[t] = fma(w[p1], v[p2], acc[t]);
                     ++t;
                 }
             }
         }
+    }
+}
+
+// Truncated 2-D integral of a Lognormal mode (ParticleDistributions.jl:614-625):
+//   H(p1,p2) = int_0^T y^{p2} f(y) [ int_0^{T-y} x^{p1} f(x) dx ] dy,  inner integral in closed form
+//   n exp(p1 μ + p1² σ²/2) Φ((ln(T-y) - μ - p1 σ²)/σ), outer integral by a fixed Gauss-Legendre rule in t = ln y.
+// (The reference nests two adaptive QuadGK calls at rtol sqrt(eps); this rule agrees with it to ~1e-10.)
+template <int MP>
+__device__ __forceinline__ void tpp_lognormal_H(double (&acc)[MP * (MP + 1) / 2], const double* __restrict__ gl, const int gl_n, const double n,
+                                                const double mu, const double sg, const double Tthr) {
+    constexpr int T = MP * (MP + 1) / 2;
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[t] = 0.0;
+    const double s2 = sg * sg;
+    const double hi = fmin(log(Tthr), mu + (double)(MP - 1) * s2 + 12.0 * sg);
+    const double lo = mu - 12.0 * sg;
+    const bool ok = hi > lo;
+    const double half = ok ? 0.5 * (hi - lo) : 0.0, mid = 0.5 * (hi + lo);
+    const double inv_sg = 1.0 / sg;
+    const double pref = n * inv_sg * 0.3989422804014327;  // n / (σ sqrt(2π))
+    double Cp[MP];
+#pragma unroll
+    for (int p = 0; p < MP; ++p) Cp[p] = n * exp((double)p * mu + (double)(p * p) * s2 / 2);
+    for (int q = 0; q < gl_n; ++q) {
+        const double t = fma(half, gl[q], mid);
+        const double y = exp(t);
+        const double d = (t - mu) * inv_sg;
+        const double wq = gl[gl_n + q] * half * pref * exp(-0.5 * d * d);  // weight * f(y) y
+        const double rem = Tthr - y;
+        const double lr = log(fmax(rem, 1e-300));
+        double in[MP];
+#pragma unroll
+        for (int p = 0; p < MP; ++p) in[p] = (rem > 0.0) ? Cp[p] * norm_cdf((lr - mu - (double)p * s2) * inv_sg) : 0.0;
+        double yp = wq;
+        int tt[MP];
+#pragma unroll
+        for (int p2 = 0; p2 < MP; ++p2) {
+#pragma unroll
+            for (int p1 = 0; p1 <= p2; ++p1) acc[tri_ct(p1, p2, MP)] = fma(yp, in[p1], acc[tri_ct(p1, p2, MP)]);
+            yp *= y;
+        }
+        (void)tt;
     }
 }
 
@@ -268,62 +344,22 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
             double s1[3], s2[3];
             const int n2d = cfg.n2d[i];
             bool done = false;
-            if (i < N - 1 && cfg.quad[i]) {
+            if (i < N - 1 && (cfg.quad[i] || cfg.ln_thr[i])) {
                 const double nmd = pn[i], th = pa[i], k = pb[i];
                 const bool skip = (nmd == 0.0) || cell_empty || !live;
                 if (!__all_sync(0xffffffffu, skip)) {
                     const int Mp = cfg.Mp[i];
-                    const double inv_th = 1.0 / th;
-                    const double log_th = log(th);
-                    const double gk = (cfg.kind[i] == CLOUDY_GAMMA) ? tgamma(k) : 1.0;
-                    const double a_top = k + (double)(Mp - 1);
-                    // own series degree / continued-fraction depth; loop bounds are the warp maxima
-                    const double X = cfg.thr[i] * inv_th;
-                    const int ai = series_a_bin(a_top);
-                    const double ser_lim = sh.serlim[ai];
-                    const int zi = series_z_bin(fmin(X, ser_lim - 0.5));
-                    const int deg = skip ? 1 : max((int)sh.deg[zi][ai], 1);
-                    const int deg_w = __reduce_max_sync(0xffffffffu, deg);
-                    const int cfd = sh.cfd[ai];
-                    const int cfd_w = __reduce_max_sync(0xffffffffu, cfd);
-                    {   // c_n = 1/(a)_{n+1}: one division, then c_{n-1} = c_n (a+n)
-                        double prod = 1.0;
-                        for (int nn = 0; nn <= deg; ++nn) prod *= (a_top + (double)nn);
-                        double cc = 1.0 / prod;
-                        for (int nn = deg; nn >= 0; --nn) {
-                            myCt[nn * TPP_THREADS] = cc;
-                            cc *= (a_top + (double)nn);
-                        }
-                        for (int nn = deg + 1; nn <= deg_w; ++nn) myCt[nn * TPP_THREADS] = 0.0;
-                    }
-                    const double pre0 = nmd * nmd / (gk * gk);
-                    const double* tb = sTab + cfg.tab_off[i];
-                    const int nb = cfg.n_bins[i];
-                    auto finish = [&](auto mp_tag) {
+                    // contraction of the truncated integrals H (raw quadrature sums scaled by `scale[p2]`) into S1, S2
+                    auto contract = [&](auto mp_tag, auto& F, const double* scale) {
                         constexpr int MP = decltype(mp_tag)::value;
-                        constexpr int T = MP * (MP + 1) / 2;
-                        double ia[MP];
-                        double gam_top = gk;
-#pragma unroll
-                        for (int pp = 0; pp < MP - 1; ++pp) {
-                            ia[pp] = 1.0 / (k + (double)pp);
-                            gam_top *= (k + (double)pp);  // Γ(k+MP-1)
-                        }
-                        ia[MP - 1] = 0.0;
-                        double F[T];
-                        tpp_nodes<MP>(F, tb, nb, k, inv_th, log_th, X, gam_top, ia, myCtc, deg_w, cfd_w, cfd, a_top, ser_lim);
-                        // F = 0 | min(Mom*Mom, H), H = n^2 θ^{p2}/Γ(k)^2 * sum — Coalescence.jl:212-227
-                        double thp[MP];
-                        thp[0] = pre0;
-#pragma unroll
-                        for (int pp = 1; pp < MP; ++pp) thp[pp] = thp[pp - 1] * th;
+                        // F = 0 | min(Mom*Mom, H) — Coalescence.jl:212-227
 #pragma unroll
                         for (int p1 = 0; p1 < MP; ++p1)
 #pragma unroll
                             for (int p2 = p1; p2 < MP; ++p2) {
                                 const int t = tri_ct(p1, p2, MP);
                                 const double mm = mom[i][p1] * mom[i][p2];
-                                const double H = thp[p2] * F[t];
+                                const double H = scale[p2] * F[t];
                                 F[t] = (mm < kEps) ? 0.0 : jl_min(mm, H);
                             }
                         tpp_s_terms<P>(cfg, i, mom[i], [&](int x, int y) -> double {
@@ -331,14 +367,90 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
                             return (x <= y) ? F[tri_ct(x < MP ? x : 0, y < MP ? y : 0, MP)] : F[tri_ct(y < MP ? y : 0, x < MP ? x : 0, MP)];
                         }, s1, s2);
                     };
-                    if (Mp == M) finish(std::integral_constant<int, M>{});
-                    else finish(std::integral_constant<int, M - 1>{});
+                    if (cfg.ln_thr[i]) {
+                        // Lognormal: (n, μ, σ) = (nmd, th, k)
+                        auto finish_ln = [&](auto mp_tag) {
+                            constexpr int MP = decltype(mp_tag)::value;
+                            double F[MP * (MP + 1) / 2];
+                            tpp_lognormal_H<MP>(F, sTab + cfg.gl_off, cfg.gl_n, nmd, th, k, cfg.thr[i]);
+                            double one[MP];
+#pragma unroll
+                            for (int pp = 0; pp < MP; ++pp) one[pp] = 1.0;
+                            contract(mp_tag, F, one);
+                        };
+                        if (Mp == M) finish_ln(std::integral_constant<int, M>{});
+                        else finish_ln(std::integral_constant<int, M - 1>{});
+                    } else {
+                        const double inv_th = 1.0 / th;
+                        const double log_th = log(th);
+                        const double gk = (cfg.kind[i] == CLOUDY_GAMMA) ? tgamma(k) : 1.0;
+                        const double a_top = k + (double)(Mp - 1);
+                        // threshold: run-constant, or this parcel's own percentile (compute_threshold, ParticleDistributions.jl:747-761)
+                        double thr = cfg.thr[i];
+                        MovingGrid mg;
+                        mg.nb = 3; mg.x_min = 0.0; mg.dx = 0.0; mg.T = 1.0;
+                        if (cfg.thr_style == CLOUDY_MOVING_THRESHOLD) {
+                            const double pct = cfg.thr[i];
+                            const double Xp = (cfg.kind[i] == CLOUDY_GAMMA) ? igam_inv(k, pct) : -log(1.0 - pct);
+                            thr = fmax(th * Xp, 1e-18);
+                            const double x_lb = fmin(1e-5, 1e-5 * thr);
+                            const double nbf = floor((double)cfg.bins_per_log_unit * log10(thr / x_lb) + 1e-10);
+                            mg.nb = (nbf >= 3.0 && nbf < 65536.0) ? (int)nbf : 3;
+                            mg.x_min = log(x_lb);
+                            mg.dx = (log(thr) - mg.x_min) / (double)mg.nb;
+                            mg.T = thr;
+                        }
+                        // own series degree / continued-fraction depth; loop bounds are the warp maxima
+                        const double X = thr * inv_th;
+                        const int ai = series_a_bin(a_top);
+                        const double ser_lim = sh.serlim[ai];
+                        const int zi = series_z_bin(fmin(X, ser_lim - 0.5));
+                        const int deg = skip ? 1 : max((int)sh.deg[zi][ai], 1);
+                        const int deg_w = __reduce_max_sync(0xffffffffu, deg);
+                        const int cfd = sh.cfd[ai];
+                        const int cfd_w = __reduce_max_sync(0xffffffffu, cfd);
+                        {   // c_n = 1/(a)_{n+1}: one division, then c_{n-1} = c_n (a+n)
+                            double prod = 1.0;
+                            for (int nn = 0; nn <= deg; ++nn) prod *= (a_top + (double)nn);
+                            double cc = 1.0 / prod;
+                            for (int nn = deg; nn >= 0; --nn) {
+                                myCt[nn * TPP_THREADS] = cc;
+                                cc *= (a_top + (double)nn);
+                            }
+                            for (int nn = deg + 1; nn <= deg_w; ++nn) myCt[nn * TPP_THREADS] = 0.0;
+                        }
+                        const double pre0 = nmd * nmd / (gk * gk);
+                        auto finish = [&](auto mp_tag) {
+                            constexpr int MP = decltype(mp_tag)::value;
+                            double ia[MP];
+                            double gam_top = gk;
+#pragma unroll
+                            for (int pp = 0; pp < MP - 1; ++pp) {
+                                ia[pp] = 1.0 / (k + (double)pp);
+                                gam_top *= (k + (double)pp);  // Γ(k+MP-1)
+                            }
+                            ia[MP - 1] = 0.0;
+                            double F[MP * (MP + 1) / 2];
+                            if (cfg.thr_style == CLOUDY_MOVING_THRESHOLD)
+                                tpp_nodes<MP>(F, mg, k, inv_th, log_th, X, gam_top, ia, myCtc, deg_w, cfd_w, cfd, a_top, ser_lim);
+                            else
+                                tpp_nodes<MP>(F, TableGrid(sTab + cfg.tab_off[i], cfg.n_bins[i]), k, inv_th, log_th, X, gam_top, ia, myCtc, deg_w,
+                                              cfd_w, cfd, a_top, ser_lim);
+                            double thp[MP];  // H = n^2 θ^{p2}/Γ(k)^2 * sum
+                            thp[0] = pre0;
+#pragma unroll
+                            for (int pp = 1; pp < MP; ++pp) thp[pp] = thp[pp - 1] * th;
+                            contract(mp_tag, F, thp);
+                        };
+                        if (Mp == M) finish(std::integral_constant<int, M>{});
+                        else finish(std::integral_constant<int, M - 1>{});
+                    }
                     done = true;
                 }
             }
             if (!done) {
                 const bool mono = (i < N - 1) && cfg.mono_thr[i];
-                const bool quad_skipped = (i < N - 1) && cfg.quad[i];  // whole warp empty: F = 0
+                const bool quad_skipped = (i < N - 1) && (cfg.quad[i] || cfg.ln_thr[i]);  // whole warp empty: F = 0
                 const double th = pa[i], nn = pn[i];
                 const bool below = th < cfg.thr[i] / 2;
                 tpp_s_terms<P>(cfg, i, mom[i], [&](int x, int y) -> double {

@@ -153,3 +153,44 @@ def mono_gamma(n_parcels=1024, seed=SEED0 + 45):
     m = np.concatenate([_moments_from_params(L.MONODISPERSE, n1, th1, None, 2), _moments_from_params(L.GAMMA, n2, th2, k2, 3)], axis=1)
     m[0] = np.array([1e7, 1e-3, 1e5, 1e-4, 2e-13]) / _norm_factors(NProgMoms, NORMS)
     return par, m * _norm_factors(NProgMoms, NORMS)
+
+
+def moving_four_modes(n_parcels=512, seed=SEED0 + 46):
+    """MovingThreshold, 4 Gamma modes, percentiles (0.99, 0.99, 0.99, 1.0) (box_gamma_mix_moving.jl:14-44)."""
+    from .coalescence import MovingThreshold
+    rng = np.random.default_rng(seed)
+    NProgMoms = (3, 3, 3, 3)
+    pd = (Gam(1e8, 1e-10, 1.0), Gam(0.0, 1e-8, 1.0), Gam(0.0, 1e-6, 1.0), Gam(0.0, 1e-4, 1.0))
+    cd = CoalescenceData(linear_tensor(5.0), NProgMoms, (0.99, 0.99, 0.99, 1.0), NORMS, MovingThreshold())
+    par = ModelParameters(pdists=pd, coal_data=cd, NProgMoms=NProgMoms, norms=NORMS, dt=1.0)
+    cols = []
+    for (nlo, nhi, tlo, thi) in ((1e1, 1e3, 0.03, 0.3), (1e-3, 1e0, 3.0, 30.0), (1e-6, 1e-3, 3e2, 3e3), (1e-9, 1e-6, 3e4, 3e5)):
+        n = _logu(rng, nlo, nhi, n_parcels); th = _logu(rng, tlo, thi, n_parcels); k = _logu(rng, 0.5, 5.0, n_parcels)
+        cols.append(_moments_from_params(L.GAMMA, n, th, k, 3))
+    m = np.concatenate(cols, axis=1)
+    m[0] = np.array([1e8, 1e-2, 2e-12, 0, 0, 0, 0, 0, 0, 0, 0, 0]) / _norm_factors(NProgMoms, NORMS)  # the script's own IC
+    m[1, 6:] = 0.0   # two trailing modes empty
+    return par, m * _norm_factors(NProgMoms, NORMS)
+
+
+def moving_gamma_exp(n_parcels=512, seed=SEED0 + 47, percentile=0.97):
+    """MovingThreshold with a Gamma cloud and an Exponential rain mode (default percentile of compute_thresholds)."""
+    from .coalescence import MovingThreshold
+    par, m = c2_gamma_exp(n_parcels, seed=seed)
+    cd = CoalescenceData(linear_tensor(5.0), par.NProgMoms, (percentile, 1.0), NORMS, MovingThreshold())
+    par2 = ModelParameters(pdists=par.pdists, coal_data=cd, NProgMoms=par.NProgMoms, norms=NORMS, dt=1.0)
+    return par2, m
+
+
+def lognormal_mixture(n_parcels=256, seed=SEED0 + 48):
+    """Two Lognormal modes, the first with a finite threshold (box_lognorm_mixture.jl:14-28)."""
+    rng = np.random.default_rng(seed)
+    NProgMoms = (3, 3)
+    pd = (LogN(1e7, -23.37, 0.833), LogN(1e5, -21.07, 0.833))
+    cd = CoalescenceData(linear_tensor(5.0), NProgMoms, (5e-10, math.inf), NORMS)
+    par = ModelParameters(pdists=pd, coal_data=cd, NProgMoms=NProgMoms, norms=NORMS, dt=1.0)
+    n1 = _logu(rng, 1e0, 1e2, n_parcels); mu1 = rng.uniform(math.log(0.03), math.log(0.4), n_parcels); s1 = rng.uniform(0.3, 1.0, n_parcels)
+    n2 = _logu(rng, 1e-3, 1e0, n_parcels); mu2 = rng.uniform(math.log(0.5), math.log(5.0), n_parcels); s2 = rng.uniform(0.3, 1.0, n_parcels)
+    m = np.concatenate([_moments_from_params(L.LOGNORMAL, n1, mu1, s1, 3), _moments_from_params(L.LOGNORMAL, n2, mu2, s2, 3)], axis=1)
+    m[0] = np.array([1e7, 1e-3, 2e-13, 1e5, 1e-4, 2e-13]) / _norm_factors(NProgMoms, NORMS)
+    return par, m * _norm_factors(NProgMoms, NORMS)
