@@ -88,7 +88,7 @@ __device__ __forceinline__ void node_integrals(double (&acc)[MPMAX * (MPMAX + 1)
     const double* ELL = tb + nb;
     const double* TMX = tb + 2 * nb;
     const double* LZ = tb + 3 * nb;
-    const double* W = tb + 4 * nb;
+    const double* W = tb + 5 * nb;  // (row 4 holds the near-node Taylor degrees of the thread-per-parcel kernel)
     const double a_top = k + (double)(Mp - 1);
     const int batches = (nb + LANES * NPL - 1) / (LANES * NPL);
     for (int bt = 0; bt < batches; ++bt) {
@@ -1064,6 +1064,22 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
             tab.insert(tab.end(), ell.begin(), ell.end());
             tab.insert(tab.end(), tmx.begin(), tmx.end());
             tab.insert(tab.end(), lz.begin(), lz.end());
+            {   // near/far split and node-only Taylor degrees of the thread-per-parcel kernel (tpp_kernel.cuh, tpp_nodes)
+                static const double rho_thr[] = {1e-5, 1e-4, 1e-3, 3e-3, 1e-2, 2e-2, 3e-2, 5e-2, 7e-2, 0.1};
+                static const int k_of[] = {4, 5, 7, 9, 11, 14, 16, 19, 22, 25};
+                std::vector<double> kd(nb, (double)TPP_TAYLOR_MAX);
+                int j_far = nb;
+                for (int j = 0; j < nb; ++j) {
+                    const double rho = xj[j] / T;
+                    if (rho > 0.1 * (1.0 + 1e-9)) { j_far = std::min(j_far, j); continue; }
+                    const double rr = 1.15 * rho;  // |z/X_c - 1| <= 1.15 rho when the centre is capped at the series limit
+                    int kk = TPP_TAYLOR_MAX;
+                    for (int q = 0; q < 10; ++q) if (rr <= rho_thr[q]) { kk = k_of[q]; break; }
+                    kd[j] = (double)kk;
+                }
+                d.j_far[i] = j_far;
+                tab.insert(tab.end(), kd.begin(), kd.end());
+            }
             for (int p = 0; p < d.M; ++p)
                 for (int j = 0; j < nb; ++j) tab.push_back(w[j] * cfg->dx[i] * pow(xj[j], (double)p));
             mpmax = std::max(mpmax, d.Mp[i]);

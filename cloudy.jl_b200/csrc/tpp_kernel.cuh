@@ -21,16 +21,39 @@ namespace cloudy {
 constexpr int TPP_THREADS = 128;
 constexpr int TPP_NPL = 5;       // 75 nodes (every threshold <= 1 in normalised units) = 15 batches exactly
 constexpr int TPP_CT_ROWS = 64;  // series coefficients c_0..c_63
+constexpr int TPP_TAYLOR_MAX = 26;  // Taylor coefficients t_0..t_26 of the near-node expansion
 
 __host__ __device__ constexpr int tri_ct(int p1, int p2, int MP) { return p1 * MP - (p1 * (p1 - 1)) / 2 + (p2 - p1); }
+
+// exp(x) for the node weights: x = n ln2/32 + r, exp(x) = 2^(n>>5) * 2^((n&31)/32) * e^r with a 32-entry table in shared
+// memory and a degree-6 polynomial on |r| <= ln2/64 (truncation 3e-18).  Arguments below -708 return ~3e-308 (the
+// callers only need "negligible"), NaN propagates.  ~11 FP64 instructions instead of ~20 for the library exp.
+__device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab32) {
+    const double xc = fmin(fmax(x, -708.0), 709.0);
+    const double t = fma(xc, 46.16624130844683, 6755399441055744.0);  // 32/ln2, 1.5*2^52
+    const int n = __double2loint(t);
+    const double nf = t - 6755399441055744.0;
+    double r = fma(nf, -0.021660849390173098, xc);   // ln2/32, high 33 bits (nf * hi is exact)
+    r = fma(nf, -2.325192846878874e-12, r);           // ln2/32, low part
+    double p = fma(r, 1.3888888888888889e-03, 8.3333333333333332e-03);
+    p = fma(p, r, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    p *= tab32[n & 31];
+    const double res = __hiloint2double(__double2hiint(p) + ((n >> 5) << 20), __double2loint(p));
+    return (x == x) ? res : x;
+}
 
 // ------------------------------------------------------------------------------------------------
 // node grids of the reference's log-spaced Simpson rule (ParticleDistributions.jl:579-585, :698-710)
 // ------------------------------------------------------------------------------------------------
 struct TableGrid {  // FixedThreshold: one grid per mode, built on the host, broadcast from shared memory
-    const double* XJ; const double* ELL; const double* TMX; const double* LZ; const double* W;
+    const double* XJ; const double* ELL; const double* TMX; const double* LZ; const double* KDEG; const double* W;
     int nb;
-    __device__ __forceinline__ TableGrid(const double* tb, int n) : XJ(tb), ELL(tb + n), TMX(tb + 2 * n), LZ(tb + 3 * n), W(tb + 4 * n), nb(n) {}
+    __device__ __forceinline__ TableGrid(const double* tb, int n)
+        : XJ(tb), ELL(tb + n), TMX(tb + 2 * n), LZ(tb + 3 * n), KDEG(tb + 4 * n), W(tb + 5 * n), nb(n) {}
     __device__ __forceinline__ int count() const { return nb; }
     __device__ __forceinline__ double tmx(int j) const { return TMX[j]; }
     __device__ __forceinline__ double log_sum(int j) const { return ELL[j] + LZ[j]; }  // ln x_j + ln(x_th - x_j)
@@ -68,11 +91,20 @@ struct MovingGrid {  // MovingThreshold: the grid follows the parcel's own thres
 // Continued-fraction regime (z beyond the series limit): gamma(k+p, z) = Γ(a_top) A_p + E h_p with
 //   h_top = -z^{MP-1} Q/P, A_top = 1, A_p = A_{p+1}/(k+p); needs g_j on its own (a second exponential).
 // ------------------------------------------------------------------------------------------------
-template <int MP, typename Grid>
+// Evaluation of the series factor S(z) = sum_n c_n z^n = gamma(a,z) z^-a e^z at the nodes:
+//   FAR nodes (x_j/x_th > 0.1, the last ~14 of 75): Horner on the parcel's c_n table at z_j.
+//   NEAR nodes (all others cluster just below X_c = min(x_th/θ, series limit)): S obeys z S' = (z - a) S + 1, so its
+//     Taylor coefficients about X_c in the relative variable r = z/X_c - 1 follow from S(X_c) alone by
+//       t_0 = S(X_c), t_1 = (X_c - a) t_0 + 1, t_{m+1} = [(X_c - a - m) t_m + X_c t_{m-1}]/(m+1),
+//     and S(z_j) = sum_{m<=K_j} t_m r^m with a node-only degree K_j = 4..25 (vs 40-60 series terms); the t_m overwrite
+//     the parcel's table column once the far nodes are done.  |r| <= 0.115 and |z - X_c| <= 2.6 bound the alternating
+//     cancellation to ~1e-14 (tables from a 40-digit search).
+template <int MP, bool TAYLOR, typename Grid>
 __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], const Grid grid, const double k,
                                           const double inv_th, const double log_th, const double X, const double gam_top,
-                                          const double (&ia)[MP], const double* __restrict__ myCt, const int deg_w, const int cfd_w,
-                                          const int cfd, const double a_top, const double ser_lim) {
+                                          const double (&ia)[MP], double* __restrict__ myCt, const int deg_w, const int cfd_w,
+                                          const int cfd, const double a_top, const double ser_lim, const int j_far,
+                                          const double* __restrict__ kdeg, const double* __restrict__ exp_tab) {
     constexpr int T = MP * (MP + 1) / 2;
     constexpr int NPL = TPP_NPL;
 #pragma unroll
@@ -84,7 +116,11 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
     A[MP - 1] = gam_top;
 #pragma unroll
     for (int p = MP - 2; p >= 0; --p) A[p] = A[p + 1] * ia[p];
-    for (int j0 = 0; j0 < nb_w; j0 += NPL) {
+    const double Xc = fmin(X, ser_lim - 0.5);      // Taylor centre (inside the series regime)
+    const double inv_Xc = 1.0 / Xc;
+
+    // one batch of NPL nodes starting at j0; `near` selects the Taylor evaluation for the series-regime nodes
+    auto batch = [&](const int j0, const int j_end, const bool near) {
         double z[NPL], h[NPL];
         bool any_ser = false, any_cf = false;
 #pragma unroll
@@ -95,7 +131,21 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
             any_cf = any_cf || !(z[i] < ser_lim);
             h[i] = 0.0;
         }
-        if (__any_sync(0xffffffffu, any_ser)) {
+        if (near) {
+            const int K = (int)kdeg[min(j0 + NPL - 1, j_end - 1)];  // node-only degree: same for every parcel
+            double r[NPL];
+            const double t_top = myCt[K * TPP_THREADS];
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) {
+                r[i] = (z[i] - Xc) * inv_Xc;
+                h[i] = t_top;
+            }
+            for (int m = K - 1; m >= 0; --m) {
+                const double tm = myCt[m * TPP_THREADS];
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], r[i], tm);
+            }
+        } else if (__any_sync(0xffffffffu, any_ser)) {
             // Horner from the warp's largest degree; the own table is zero above the parcel's own degree, so the
             // result does not depend on the neighbours
             const double c_top = myCt[deg_w * TPP_THREADS];
@@ -150,8 +200,8 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
         for (int i = 0; i < NPL; ++i) {
             const int jraw = j0 + i;
             const int j = min(jraw, nb - 1);
-            double gE = exp(fma(k, grid.log_sum(j), e0));  // g_j * E_j
-            gE = (jraw < nb) ? gE : 0.0;
+            double gE = fast_exp(fma(k, grid.log_sum(j), e0), exp_tab);  // g_j * E_j
+            gE = (jraw < j_end && jraw < nb) ? gE : 0.0;
             double zp[MP];
             zp[0] = 1.0;
 #pragma unroll
@@ -167,7 +217,7 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
             if (warp_cf) {
                 const bool cf_i = !(z[i] < ser_lim);
                 double g = exp(fma(k, grid.ell(j) - log_th, -(grid.x(j) * inv_th)));  // (x_j/θ)^k e^{-x_j/θ}
-                g = (cf_i && jraw < nb) ? g : 0.0;
+                g = (cf_i && jraw < j_end && jraw < nb) ? g : 0.0;
 #pragma unroll
                 for (int p = 0; p < MP; ++p) v[p] = fma(g, A[p], v[p]);
             }
@@ -183,6 +233,32 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
                 }
             }
         }
+    };
+
+    // far nodes first (they need the c_n table), then S(X_c) from the same table, its Taylor coefficients into the
+    // table column, and the near nodes.  One loop so that the batch body is instantiated once (instruction cache).
+    const int jf = TAYLOR ? j_far : 0;
+    const int n_far = (nb_w - jf + NPL - 1) / NPL;
+    const int n_near = TAYLOR ? (jf + NPL - 1) / NPL : 0;
+    for (int bt = 0; bt < n_far + n_near; ++bt) {
+        const bool near = bt >= n_far;
+        if (TAYLOR && bt == n_far) {
+            double s0 = myCt[deg_w * TPP_THREADS];
+            for (int n = deg_w - 1; n >= 0; --n) s0 = fma(s0, Xc, myCt[n * TPP_THREADS]);
+            const double Xa = Xc - a_top;
+            double tm1 = s0, tm = fma(Xa, s0, 1.0);
+            myCt[0] = tm1;
+            myCt[TPP_THREADS] = tm;
+#pragma unroll
+            for (int m = 1; m < TPP_TAYLOR_MAX; ++m) {
+                const double tn = fma(Xa - (double)m, tm, Xc * tm1) * (1.0 / (double)(m + 1));
+                myCt[(m + 1) * TPP_THREADS] = tn;
+                tm1 = tm;
+                tm = tn;
+            }
+        }
+        const int j0 = near ? (bt - n_far) * NPL : jf + bt * NPL;
+        batch(j0, near ? jf : nb_w, near);
     }
 }
 
@@ -262,6 +338,7 @@ __device__ __forceinline__ void tpp_s_terms(const DevConfig& cfg, const int k, c
 struct TppShared {
     unsigned char deg[kSerZ][kSerA];
     double serlim[kSerA];
+    double exp32[32];  // 2^(i/32)
     int cfd[kSerA];
 };
 
@@ -277,6 +354,7 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
     for (int i = tid; i < cfg.tab_total; i += TPP_THREADS) sTab[i] = cfg.tab[i];
     for (int i = tid; i < kSerZ * kSerA; i += TPP_THREADS) sh.deg[i / kSerA][i % kSerA] = kSeriesDeg2[i / kSerA][i % kSerA];
     if (tid < kSerA) { sh.cfd[tid] = kCfDepth[tid]; sh.serlim[tid] = kSeriesLimit[tid]; }
+    if (tid < 32) sh.exp32[tid] = exp2((double)tid / 32.0);
     __syncthreads();
     const double* myCtc = sCt + tid;
     double* myCt = sCt + tid;
@@ -431,11 +509,13 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
                             }
                             ia[MP - 1] = 0.0;
                             double F[MP * (MP + 1) / 2];
-                            if (cfg.thr_style == CLOUDY_MOVING_THRESHOLD)
-                                tpp_nodes<MP>(F, mg, k, inv_th, log_th, X, gam_top, ia, myCtc, deg_w, cfd_w, cfd, a_top, ser_lim);
-                            else
-                                tpp_nodes<MP>(F, TableGrid(sTab + cfg.tab_off[i], cfg.n_bins[i]), k, inv_th, log_th, X, gam_top, ia, myCtc, deg_w,
-                                              cfd_w, cfd, a_top, ser_lim);
+                            if (cfg.thr_style == CLOUDY_MOVING_THRESHOLD) {
+                                tpp_nodes<MP, false>(F, mg, k, inv_th, log_th, X, gam_top, ia, myCt, deg_w, cfd_w, cfd, a_top, ser_lim, 0, nullptr, sh.exp32);
+                            } else {
+                                const TableGrid tg(sTab + cfg.tab_off[i], cfg.n_bins[i]);
+                                tpp_nodes<MP, true>(F, tg, k, inv_th, log_th, X, gam_top, ia, myCt, deg_w, cfd_w, cfd, a_top, ser_lim, cfg.j_far[i],
+                                                    tg.KDEG, sh.exp32);
+                            }
                             double thp[MP];  // H = n^2 θ^{p2}/Γ(k)^2 * sum
                             thp[0] = pre0;
 #pragma unroll
