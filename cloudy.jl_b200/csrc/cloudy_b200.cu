@@ -88,7 +88,7 @@ __device__ __forceinline__ void node_integrals(double (&acc)[MPMAX * (MPMAX + 1)
     const double* ELL = tb + nb;
     const double* TMX = tb + 2 * nb;
     const double* LZ = tb + 3 * nb;
-    const double* W = tb + 5 * nb;  // (row 4 holds the near-node Taylor degrees of the thread-per-parcel kernel)
+    const double* W = tb + 4 * nb;
     const double a_top = k + (double)(Mp - 1);
     const int batches = (nb + LANES * NPL - 1) / (LANES * NPL);
     for (int bt = 0; bt < batches; ++bt) {
@@ -1064,24 +1064,44 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
             tab.insert(tab.end(), ell.begin(), ell.end());
             tab.insert(tab.end(), tmx.begin(), tmx.end());
             tab.insert(tab.end(), lz.begin(), lz.end());
-            {   // near/far split and node-only Taylor degrees of the thread-per-parcel kernel (tpp_kernel.cuh, tpp_nodes)
+            for (int p = 0; p < d.M; ++p)
+                for (int j = 0; j < nb; ++j) tab.push_back(w[j] * cfg->dx[i] * pow(xj[j], (double)p));
+            {   // packed node records of the thread-per-parcel kernel: [near | far], each padded to a multiple of TPP_NPL
                 static const double rho_thr[] = {1e-5, 1e-4, 1e-3, 3e-3, 1e-2, 2e-2, 3e-2, 5e-2, 7e-2, 0.1};
                 static const int k_of[] = {4, 5, 7, 9, 11, 14, 16, 19, 22, 25};
-                std::vector<double> kd(nb, (double)TPP_TAYLOR_MAX);
-                int j_far = nb;
+                const int R = 5 + d.M;
+                auto push_node = [&](int j, double kdeg, bool dummy) {
+                    tab.push_back(tmx[j]);  // dummies reuse a real node's position (zero weights)
+                    tab.push_back(ell[j] + lz[j]);
+                    tab.push_back(ell[j]);
+                    tab.push_back(xj[j]);
+                    tab.push_back(kdeg);
+                    for (int p = 0; p < d.M; ++p) tab.push_back(dummy ? 0.0 : w[j] * cfg->dx[i] * pow(xj[j], (double)p));
+                };
+                d.rec_off[i] = (int)tab.size();
+                int n_near = 0, n_far = 0;
+                double kmax = 4.0;
                 for (int j = 0; j < nb; ++j) {
                     const double rho = xj[j] / T;
-                    if (rho > 0.1 * (1.0 + 1e-9)) { j_far = std::min(j_far, j); continue; }
+                    if (rho > 0.1 * (1.0 + 1e-9)) continue;
                     const double rr = 1.15 * rho;  // |z/X_c - 1| <= 1.15 rho when the centre is capped at the series limit
                     int kk = TPP_TAYLOR_MAX;
                     for (int q = 0; q < 10; ++q) if (rr <= rho_thr[q]) { kk = k_of[q]; break; }
-                    kd[j] = (double)kk;
+                    kmax = std::max(kmax, (double)kk);
+                    push_node(j, (double)kk, false);
+                    ++n_near;
                 }
-                d.j_far[i] = j_far;
-                tab.insert(tab.end(), kd.begin(), kd.end());
+                while (n_near % TPP_NPL) { push_node(0, kmax, true); ++n_near; }
+                for (int j = 0; j < nb; ++j) {
+                    if (!(xj[j] / T > 0.1 * (1.0 + 1e-9))) continue;
+                    push_node(j, 0.0, false);
+                    ++n_far;
+                }
+                while (n_far % TPP_NPL) { push_node(nb - 1, 0.0, true); ++n_far; }
+                d.rec_near[i] = n_near;
+                d.rec_far[i] = n_far;
+                (void)R;
             }
-            for (int p = 0; p < d.M; ++p)
-                for (int j = 0; j < nb; ++j) tab.push_back(w[j] * cfg->dx[i] * pow(xj[j], (double)p));
             mpmax = std::max(mpmax, d.Mp[i]);
         }
     }

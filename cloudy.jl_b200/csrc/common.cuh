@@ -31,7 +31,7 @@ struct DevConfig {
     int gl_off, gl_n;              // Gauss-Legendre nodes/weights on [-1,1] inside `tab` (nodes then weights)
     int bins_per_log_unit;         // MovingThreshold: per-parcel grid density (15 in the reference)
     int n_bins[MAXN], tab_off[MAXN];
-    int j_far[MAXN];               // first node with x_j/x_th > 0.1 (far nodes use the series, near nodes the Taylor form)
+    int rec_off[MAXN], rec_near[MAXN], rec_far[MAXN];  // packed node records of the thread-per-parcel kernel (tpp_kernel.cuh)
     int tab_total;                 // doubles of grid tables to stage in shared memory
     int n_vel, nz;
     double c[MAXN][MAXN][MAXP][MAXP];

@@ -26,10 +26,10 @@ constexpr int TPP_TAYLOR_MAX = 26;  // Taylor coefficients t_0..t_26 of the near
 __host__ __device__ constexpr int tri_ct(int p1, int p2, int MP) { return p1 * MP - (p1 * (p1 - 1)) / 2 + (p2 - p1); }
 
 // exp(x) for the node weights: x = n ln2/32 + r, exp(x) = 2^(n>>5) * 2^((n&31)/32) * e^r with a 32-entry table in shared
-// memory and a degree-6 polynomial on |r| <= ln2/64 (truncation 3e-18).  Arguments below -708 return ~3e-308 (the
-// callers only need "negligible"), NaN propagates.  ~11 FP64 instructions instead of ~20 for the library exp.
+// memory and a degree-6 polynomial on |r| <= ln2/64 (truncation 3e-18).  Valid for x <= 700 (the node weights' exponents
+// are bounded by ~k ln k); arguments below -708 return 0.  ~11 FP64 instructions instead of ~20 for the library exp.
 __device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab32) {
-    const double xc = fmin(fmax(x, -708.0), 709.0);
+    const double xc = x;
     const double t = fma(xc, 46.16624130844683, 6755399441055744.0);  // 32/ln2, 1.5*2^52
     const int n = __double2loint(t);
     const double nf = t - 6755399441055744.0;
@@ -43,41 +43,51 @@ __device__ __forceinline__ double fast_exp(double x, const double* __restrict__ 
     p = fma(p, r, 1.0);
     p *= tab32[n & 31];
     const double res = __hiloint2double(__double2hiint(p) + ((n >> 5) << 20), __double2loint(p));
-    return (x == x) ? res : x;
+    return (x >= -708.0) ? res : 0.0;  // underflow (and NaN, which the other factors of the integrand carry anyway) -> 0
 }
 
 // ------------------------------------------------------------------------------------------------
 // node grids of the reference's log-spaced Simpson rule (ParticleDistributions.jl:579-585, :698-710)
 // ------------------------------------------------------------------------------------------------
+// Node records of the FixedThreshold grid, packed per node so that one base address serves all loads:
+//   [0] x_th - x_j   [1] ln x_j + ln(x_th - x_j)   [2] ln x_j   [3] x_j   [4] Taylor degree K_j   [5+p] w_j dx x_j^p
+// The host orders them [near nodes | far nodes], each zone padded to a multiple of TPP_NPL with zero-weight dummy
+// nodes, so the hot loop needs no index clamps and no validity selects.
+constexpr int REC_TMX = 0, REC_LSUM = 1, REC_ELL = 2, REC_X = 3, REC_K = 4, REC_W = 5;
+
 struct TableGrid {  // FixedThreshold: one grid per mode, built on the host, broadcast from shared memory
-    const double* XJ; const double* ELL; const double* TMX; const double* LZ; const double* KDEG; const double* W;
-    int nb;
-    __device__ __forceinline__ TableGrid(const double* tb, int n)
-        : XJ(tb), ELL(tb + n), TMX(tb + 2 * n), LZ(tb + 3 * n), KDEG(tb + 4 * n), W(tb + 5 * n), nb(n) {}
-    __device__ __forceinline__ int count() const { return nb; }
-    __device__ __forceinline__ double tmx(int j) const { return TMX[j]; }
-    __device__ __forceinline__ double log_sum(int j) const { return ELL[j] + LZ[j]; }  // ln x_j + ln(x_th - x_j)
-    __device__ __forceinline__ double ell(int j) const { return ELL[j]; }
-    __device__ __forceinline__ double x(int j) const { return XJ[j]; }
+    const double* rec;
+    int stride, n_near, n_far;  // padded node counts
+    static constexpr bool kPadded = true;
+    __device__ __forceinline__ int count() const { return n_near + n_far; }
+    __device__ __forceinline__ bool valid(int) const { return true; }
+    __device__ __forceinline__ double tmx(int j) const { return rec[j * stride + REC_TMX]; }
+    __device__ __forceinline__ double log_sum(int j) const { return rec[j * stride + REC_LSUM]; }
+    __device__ __forceinline__ double ell(int j) const { return rec[j * stride + REC_ELL]; }
+    __device__ __forceinline__ double x(int j) const { return rec[j * stride + REC_X]; }
+    __device__ __forceinline__ int taylor_degree(int j) const { return (int)rec[j * stride + REC_K]; }
     template <int MP>
     __device__ __forceinline__ void weights(int j, double (&w)[MP]) const {
 #pragma unroll
-        for (int p = 0; p < MP; ++p) w[p] = W[p * nb + j];  // w_j dx x_j^p
+        for (int p = 0; p < MP; ++p) w[p] = rec[j * stride + REC_W + p];  // w_j dx x_j^p
     }
 };
 
-struct MovingGrid {  // MovingThreshold: the grid follows the parcel's own threshold
+struct MovingGrid {  // MovingThreshold: the grid follows the parcel's own threshold (ParticleDistributions.jl:579-585)
     double x_min, dx, T;
     int nb;
+    static constexpr bool kPadded = false;
     __device__ __forceinline__ int count() const { return nb; }
-    __device__ __forceinline__ double ell(int j) const { return x_min + (double)j * dx; }  // logx(x_min, j+1, dx)
+    __device__ __forceinline__ bool valid(int j) const { return j < nb; }
+    __device__ __forceinline__ double ell(int j) const { return x_min + (double)min(j, nb - 1) * dx; }  // logx(x_min, j+1, dx)
     __device__ __forceinline__ double x(int j) const { return exp(ell(j)); }
     __device__ __forceinline__ double tmx(int j) const { return T - x(j); }
     __device__ __forceinline__ double log_sum(int j) const { return ell(j) + log(tmx(j)); }
+    __device__ __forceinline__ int taylor_degree(int) const { return 0; }
     template <int MP>
     __device__ __forceinline__ void weights(int j, double (&w)[MP]) const {
         const double xj = x(j);
-        w[0] = simpson_weight(j + 1, nb) * (dx / 48.0);
+        w[0] = valid(j) ? simpson_weight(j + 1, nb) * (dx / 48.0) : 0.0;
 #pragma unroll
         for (int p = 1; p < MP; ++p) w[p] = w[p - 1] * xj;
     }
@@ -86,53 +96,66 @@ struct MovingGrid {  // MovingThreshold: the grid follows the parcel's own thres
 // ------------------------------------------------------------------------------------------------
 // node loop for one mode of one parcel: acc[t(p1,p2)] = sum_j W[p1][j] g_j gamma(k+p2, z_j)
 //   g_j = (x_j/θ)^k e^{-x_j/θ},  z_j = (x_th - x_j)/θ,  E_j = z_j^k e^{-z_j}
-// Series regime: gamma(k+p, z) = E h_p with h_top = z^{MP-1} S(z), h_p = (h_{p+1} + z^p)/(k+p), and
-//   g_j E_j = exp(k (ln x_j + ln(x_th - x_j) - 2 ln θ) - x_th/θ)   — ONE exponential per node.
-// Continued-fraction regime (z beyond the series limit): gamma(k+p, z) = Γ(a_top) A_p + E h_p with
-//   h_top = -z^{MP-1} Q/P, A_top = 1, A_p = A_{p+1}/(k+p); needs g_j on its own (a second exponential).
+// Series regime (z below the series limit): gamma(k+p, z) = E h_p with h_top = z^{MP-1} S(z),
+//   h_p = (h_{p+1} + z^p)/(k+p), and g_j E_j = exp(k (ln x_j + ln(x_th - x_j) - 2 ln θ) - x_th/θ) — ONE exponential.
+//   S(z) = sum_n c_n z^n = gamma(a,z) z^-a e^z, a = k+MP-1:
+//     FAR nodes (x_j/x_th > 0.1, the last ~14 of 75): Horner on the parcel's c_n table at z_j;
+//     NEAR nodes cluster just below X_c = min(x_th/θ, series limit - 0.5): S obeys z S' = (z - a) S + 1, so its Taylor
+//       coefficients about X_c in r = z/X_c - 1 follow from S(X_c) alone,
+//         t_0 = S(X_c), t_1 = (X_c - a) t_0 + 1, t_{m+1} = [(X_c - a - m) t_m + X_c t_{m-1}]/(m+1),
+//       and S(z_j) = sum_{m<=K_j} t_m r^m with a node-only degree K_j = 4..25 (instead of 40-60 series terms).  The t_m
+//       overwrite the parcel's table column once the far nodes are done.  |r| <= 0.115 and |z - X_c| <= 2.6 bound the
+//       alternating cancellation to ~1e-14 (degrees from a 40-digit search).
+// Continued-fraction regime (z beyond the series limit, i.e. the threshold far in the tail): the main loop uses
+//   h_top = 0 there and a separate, compact loop adds B_p (g Γ(a) - g E z^{MP-1} Q/P), B_p = prod_{q>=p} 1/(k+q), with
+//   Q/P the Legendre continued fraction of the upper function (forward recurrence, fixed depth) and g_j on its own.
 // ------------------------------------------------------------------------------------------------
-// Evaluation of the series factor S(z) = sum_n c_n z^n = gamma(a,z) z^-a e^z at the nodes:
-//   FAR nodes (x_j/x_th > 0.1, the last ~14 of 75): Horner on the parcel's c_n table at z_j.
-//   NEAR nodes (all others cluster just below X_c = min(x_th/θ, series limit)): S obeys z S' = (z - a) S + 1, so its
-//     Taylor coefficients about X_c in the relative variable r = z/X_c - 1 follow from S(X_c) alone by
-//       t_0 = S(X_c), t_1 = (X_c - a) t_0 + 1, t_{m+1} = [(X_c - a - m) t_m + X_c t_{m-1}]/(m+1),
-//     and S(z_j) = sum_{m<=K_j} t_m r^m with a node-only degree K_j = 4..25 (vs 40-60 series terms); the t_m overwrite
-//     the parcel's table column once the far nodes are done.  |r| <= 0.115 and |z - X_c| <= 2.6 bound the alternating
-//     cancellation to ~1e-14 (tables from a 40-digit search).
 template <int MP, bool TAYLOR, typename Grid>
 __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], const Grid grid, const double k,
                                           const double inv_th, const double log_th, const double X, const double gam_top,
                                           const double (&ia)[MP], double* __restrict__ myCt, const int deg_w, const int cfd_w,
-                                          const int cfd, const double a_top, const double ser_lim, const int j_far,
-                                          const double* __restrict__ kdeg, const double* __restrict__ exp_tab) {
+                                          const int cfd, const double a_top, const double ser_lim,
+                                          const double* __restrict__ exp_tab) {
     constexpr int T = MP * (MP + 1) / 2;
     constexpr int NPL = TPP_NPL;
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.0;
-    const int nb = grid.count();                               // own node count
-    const int nb_w = __reduce_max_sync(0xffffffffu, nb);      // loop bound: the warp's largest grid
-    const double e0 = fma(-2.0 * k, log_th, -X);  // exponent offset of g*E
-    double A[MP];                                  // Γ(a_top) A_p
-    A[MP - 1] = gam_top;
-#pragma unroll
-    for (int p = MP - 2; p >= 0; --p) A[p] = A[p + 1] * ia[p];
-    const double Xc = fmin(X, ser_lim - 0.5);      // Taylor centre (inside the series regime)
+    const int nb_w = Grid::kPadded ? grid.count() : __reduce_max_sync(0xffffffffu, grid.count());  // loop bound
+    const double e0 = fma(-2.0 * k, log_th, -X);   // exponent offset of g*E
+    const double Xc = fmin(X, ser_lim - 0.5);       // Taylor centre (inside the series regime)
     const double inv_Xc = 1.0 / Xc;
 
-    // one batch of NPL nodes starting at j0; `near` selects the Taylor evaluation for the series-regime nodes
-    auto batch = [&](const int j0, const int j_end, const bool near) {
-        double z[NPL], h[NPL];
-        bool any_ser = false, any_cf = false;
+    // near nodes come first in the padded tables; they are processed AFTER the far nodes (which need the c_n table)
+    int n_near_b = 0, jf = 0;
+    if constexpr (TAYLOR) {
+        jf = grid.n_near;
+        n_near_b = jf / NPL;
+    }
+    const int n_far_b = (nb_w - jf + NPL - 1) / NPL;
+    for (int bt = 0; bt < n_far_b + n_near_b; ++bt) {
+        const bool near = bt >= n_far_b;
+        if (TAYLOR && bt == n_far_b) {
+            // S(X_c) from the c_n table, then its Taylor coefficients into the same column
+            double s0 = myCt[deg_w * TPP_THREADS];
+            for (int n = deg_w - 1; n >= 0; --n) s0 = fma(s0, Xc, myCt[n * TPP_THREADS]);
+            const double Xa = Xc - a_top;
+            double tm1 = s0, tm = fma(Xa, s0, 1.0);
+            myCt[0] = tm1;
+            myCt[TPP_THREADS] = tm;
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-            const int j = min(j0 + i, nb - 1);
-            z[i] = grid.tmx(j) * inv_th;  // (x_th - x_j)/θ
-            any_ser = any_ser || (z[i] < ser_lim);
-            any_cf = any_cf || !(z[i] < ser_lim);
-            h[i] = 0.0;
+            for (int m = 1; m < TPP_TAYLOR_MAX; ++m) {
+                const double tn = fma(Xa - (double)m, tm, Xc * tm1) * (1.0 / (double)(m + 1));
+                myCt[(m + 1) * TPP_THREADS] = tn;
+                tm1 = tm;
+                tm = tn;
+            }
         }
+        const int j0 = near ? (bt - n_far_b) * NPL : jf + bt * NPL;
+        double z[NPL], h[NPL];
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) z[i] = grid.tmx(j0 + i) * inv_th;  // (x_th - x_j)/θ
         if (near) {
-            const int K = (int)kdeg[min(j0 + NPL - 1, j_end - 1)];  // node-only degree: same for every parcel
+            const int K = grid.taylor_degree(j0 + NPL - 1);  // node-only degree: the same for every parcel
             double r[NPL];
             const double t_top = myCt[K * TPP_THREADS];
 #pragma unroll
@@ -145,7 +168,7 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
 #pragma unroll
                 for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], r[i], tm);
             }
-        } else if (__any_sync(0xffffffffu, any_ser)) {
+        } else {
             // Horner from the warp's largest degree; the own table is zero above the parcel's own degree, so the
             // result does not depend on the neighbours
             const double c_top = myCt[deg_w * TPP_THREADS];
@@ -170,56 +193,22 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
                 for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], z[i], c0);
             }
         }
-        const bool warp_cf = __any_sync(0xffffffffu, any_cf);
-        if (warp_cf) {
-            // Legendre continued fraction of Gamma(a,z)/(z^a e^-z), forward recurrence, fixed depth, one node at a time
-            // (rare regime: keeps the register footprint of the common path small).  Beyond the parcel's own depth the
-            // step degenerates to P <- 1*P + 0, which is exact.
-#pragma unroll
-            for (int i = 0; i < NPL; ++i) {
-                const bool cf_i = !(z[i] < ser_lim);
-                if (__any_sync(0xffffffffu, cf_i)) {
-                    const double zc = fmin(z[i], 256.0);  // beyond this the upper function is < 1e-80 of Gamma(a)
-                    double b = zc + 1.0 - a_top;
-                    double Pm = 1.0, Pc = b, Qm = 0.0, Qc = 1.0, fn = 0.0;
-                    for (int n = 1; n <= cfd_w; ++n) {
-                        fn += 1.0;
-                        b += 2.0;
-                        const bool on = n <= cfd;
-                        const double an = on ? fn * (a_top - fn) : 0.0;  // -n(n-a)
-                        const double bb = on ? b : 1.0;
-                        const double Pn = fma(bb, Pc, an * Pm);
-                        const double Qn = fma(bb, Qc, an * Qm);
-                        Pm = Pc; Pc = Pn; Qm = Qc; Qc = Qn;
-                    }
-                    if (cf_i) h[i] = -(Qc / Pc);
-                }
-            }
-        }
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
-            const int jraw = j0 + i;
-            const int j = min(jraw, nb - 1);
-            double gE = fast_exp(fma(k, grid.log_sum(j), e0), exp_tab);  // g_j * E_j
-            gE = (jraw < j_end && jraw < nb) ? gE : 0.0;
+            const int j = j0 + i;
+            const double gE = fast_exp(fma(k, grid.log_sum(j), e0), exp_tab);  // g_j * E_j
+            const double hs = (z[i] < ser_lim) ? h[i] : 0.0;                   // continued-fraction nodes: added below
             double zp[MP];
             zp[0] = 1.0;
 #pragma unroll
             for (int p = 1; p < MP; ++p) zp[p] = zp[p - 1] * z[i];
             double v[MP];
-            double hp = zp[MP - 1] * h[i];
+            double hp = zp[MP - 1] * hs;
             v[MP - 1] = gE * hp;
 #pragma unroll
             for (int p = MP - 2; p >= 0; --p) {
                 hp = (hp + zp[p]) * ia[p];  // downward recurrence
                 v[p] = gE * hp;
-            }
-            if (warp_cf) {
-                const bool cf_i = !(z[i] < ser_lim);
-                double g = exp(fma(k, grid.ell(j) - log_th, -(grid.x(j) * inv_th)));  // (x_j/θ)^k e^{-x_j/θ}
-                g = (cf_i && jraw < j_end && jraw < nb) ? g : 0.0;
-#pragma unroll
-                for (int p = 0; p < MP; ++p) v[p] = fma(g, A[p], v[p]);
             }
             double w[MP];
             grid.template weights<MP>(j, w);
@@ -233,32 +222,53 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
                 }
             }
         }
-    };
+    }
 
-    // far nodes first (they need the c_n table), then S(X_c) from the same table, its Taylor coefficients into the
-    // table column, and the near nodes.  One loop so that the batch body is instantiated once (instruction cache).
-    const int jf = TAYLOR ? j_far : 0;
-    const int n_far = (nb_w - jf + NPL - 1) / NPL;
-    const int n_near = TAYLOR ? (jf + NPL - 1) / NPL : 0;
-    for (int bt = 0; bt < n_far + n_near; ++bt) {
-        const bool near = bt >= n_far;
-        if (TAYLOR && bt == n_far) {
-            double s0 = myCt[deg_w * TPP_THREADS];
-            for (int n = deg_w - 1; n >= 0; --n) s0 = fma(s0, Xc, myCt[n * TPP_THREADS]);
-            const double Xa = Xc - a_top;
-            double tm1 = s0, tm = fma(Xa, s0, 1.0);
-            myCt[0] = tm1;
-            myCt[TPP_THREADS] = tm;
+    // ---- rare path: nodes in the continued-fraction regime (only when x_th/θ reaches the series limit) ----
+    if (__any_sync(0xffffffffu, !(X < ser_lim))) {
+        double B[MP];
+        B[MP - 1] = 1.0;
 #pragma unroll
-            for (int m = 1; m < TPP_TAYLOR_MAX; ++m) {
-                const double tn = fma(Xa - (double)m, tm, Xc * tm1) * (1.0 / (double)(m + 1));
-                myCt[(m + 1) * TPP_THREADS] = tn;
-                tm1 = tm;
-                tm = tn;
+        for (int p = MP - 2; p >= 0; --p) B[p] = B[p + 1] * ia[p];
+#pragma unroll 1
+        for (int j = 0; j < nb_w; ++j) {
+            const double z = grid.tmx(j) * inv_th;
+            const bool cf_j = !(z < ser_lim);
+            if (!__any_sync(0xffffffffu, cf_j)) continue;
+            const double zc = fmin(z, 256.0);  // beyond this the upper function is < 1e-80 of Gamma(a)
+            double b = zc + 1.0 - a_top;
+            double Pm = 1.0, Pc = b, Qm = 0.0, Qc = 1.0, fn = 0.0;
+            for (int n = 1; n <= cfd_w; ++n) {
+                // beyond the parcel's own depth the step degenerates to P <- 1*P + 0, which is exact
+                fn += 1.0;
+                b += 2.0;
+                const bool on = n <= cfd;
+                const double an = on ? fn * (a_top - fn) : 0.0;  // -n(n-a)
+                const double bb = on ? b : 1.0;
+                const double Pn = fma(bb, Pc, an * Pm);
+                const double Qn = fma(bb, Qc, an * Qm);
+                Pm = Pc; Pc = Pn; Qm = Qc; Qc = Qn;
+            }
+            const double gE = exp(fma(k, grid.log_sum(j), e0));
+            const double g = exp(fma(k, grid.ell(j) - log_th, -(grid.x(j) * inv_th)));  // (x_j/θ)^k e^{-x_j/θ}
+            double zt = 1.0;
+#pragma unroll
+            for (int p = 1; p < MP; ++p) zt *= z;
+            double xi = fma(g, gam_top, -(gE * zt) * (Qc / Pc));
+            xi = cf_j ? xi : 0.0;
+            double w[MP];
+            grid.template weights<MP>(j, w);
+            int t = 0;
+#pragma unroll
+            for (int p1 = 0; p1 < MP; ++p1) {
+                const double wx = w[p1] * xi;
+#pragma unroll
+                for (int p2 = p1; p2 < MP; ++p2) {
+                    acc[t] = fma(wx, B[p2], acc[t]);
+                    ++t;
+                }
             }
         }
-        const int j0 = near ? (bt - n_far) * NPL : jf + bt * NPL;
-        batch(j0, near ? jf : nb_w, near);
     }
 }
 
@@ -510,11 +520,14 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
                             ia[MP - 1] = 0.0;
                             double F[MP * (MP + 1) / 2];
                             if (cfg.thr_style == CLOUDY_MOVING_THRESHOLD) {
-                                tpp_nodes<MP, false>(F, mg, k, inv_th, log_th, X, gam_top, ia, myCt, deg_w, cfd_w, cfd, a_top, ser_lim, 0, nullptr, sh.exp32);
+                                tpp_nodes<MP, false>(F, mg, k, inv_th, log_th, X, gam_top, ia, myCt, deg_w, cfd_w, cfd, a_top, ser_lim, sh.exp32);
                             } else {
-                                const TableGrid tg(sTab + cfg.tab_off[i], cfg.n_bins[i]);
-                                tpp_nodes<MP, true>(F, tg, k, inv_th, log_th, X, gam_top, ia, myCt, deg_w, cfd_w, cfd, a_top, ser_lim, cfg.j_far[i],
-                                                    tg.KDEG, sh.exp32);
+                                TableGrid tg;
+                                tg.rec = sTab + cfg.rec_off[i];
+                                tg.stride = REC_W + M;
+                                tg.n_near = cfg.rec_near[i];
+                                tg.n_far = cfg.rec_far[i];
+                                tpp_nodes<MP, true>(F, tg, k, inv_th, log_th, X, gam_top, ia, myCt, deg_w, cfd_w, cfd, a_top, ser_lim, sh.exp32);
                             }
                             double thp[MP];  // H = n^2 θ^{p2}/Γ(k)^2 * sum
                             thp[0] = pre0;
