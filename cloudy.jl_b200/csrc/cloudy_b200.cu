@@ -840,7 +840,7 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
         args.flux = ctx->flux->d;
         args.s_flux = ctx->flux->stride;
     }
-    size_t smem = sizeof(double) * (((size_t)d.tab_total + 1) / 2 * 2 + (size_t)TPP_CT_ROWS * TPP_THREADS);
+    size_t smem = sizeof(double) * (((size_t)d.tpp_total + 1) / 2 * 2 + (size_t)TPP_CT_ROWS * TPP_THREADS);
     CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, TPP_THREADS, smem));
@@ -1004,7 +1004,7 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
                     d.c[j][k][a][b] = cfg->c[j][k][a][b];
                 }
     // grid tables
-    std::vector<double> tab;
+    std::vector<double> tab, tab2;  // tab: SoA tables of the lane-cooperative kernel; tab2: records / rules of the thread-per-parcel kernel
     int mpmax = 0;
     bool any_ln = false;
     for (int i = 0; i < N; ++i) {
@@ -1071,14 +1071,14 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
                 static const int k_of[] = {4, 5, 7, 9, 11, 14, 16, 19, 22, 25};
                 const int R = 5 + d.M;
                 auto push_node = [&](int j, double kdeg, bool dummy) {
-                    tab.push_back(tmx[j]);  // dummies reuse a real node's position (zero weights)
-                    tab.push_back(ell[j] + lz[j]);
-                    tab.push_back(ell[j]);
-                    tab.push_back(xj[j]);
-                    tab.push_back(kdeg);
-                    for (int p = 0; p < d.M; ++p) tab.push_back(dummy ? 0.0 : w[j] * cfg->dx[i] * pow(xj[j], (double)p));
+                    tab2.push_back(tmx[j]);  // dummies reuse a real node's position (zero weights)
+                    tab2.push_back(ell[j] + lz[j]);
+                    tab2.push_back(ell[j]);
+                    tab2.push_back(xj[j]);
+                    tab2.push_back(kdeg);
+                    for (int p = 0; p < d.M; ++p) tab2.push_back(dummy ? 0.0 : w[j] * cfg->dx[i] * pow(xj[j], (double)p));
                 };
-                d.rec_off[i] = (int)tab.size();
+                d.rec_off[i] = (int)tab2.size();
                 int n_near = 0, n_far = 0;
                 double kmax = 4.0;
                 for (int j = 0; j < nb; ++j) {
@@ -1108,7 +1108,7 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
     if (any_ln) {
         // Gauss-Legendre rule on [-1, 1] (Newton iteration on the Legendre polynomial), nodes then weights
         const int n = 128;
-        d.gl_off = (int)tab.size();
+        d.gl_off = (int)tab2.size();
         d.gl_n = n;
         std::vector<double> xs(n), ws(n);
         for (int i = 0; i < (n + 1) / 2; ++i) {
@@ -1128,11 +1128,14 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
             xs[i] = -x; xs[n - 1 - i] = x;
             ws[i] = ws[n - 1 - i] = 2.0 / ((1.0 - x * x) * pp * pp);
         }
-        tab.insert(tab.end(), xs.begin(), xs.end());
-        tab.insert(tab.end(), ws.begin(), ws.end());
+        tab2.insert(tab2.end(), xs.begin(), xs.end());
+        tab2.insert(tab2.end(), ws.begin(), ws.end());
     }
     d.bins_per_log_unit = cfg->bins_per_log_unit > 0 ? cfg->bins_per_log_unit : 15;
     d.tab_total = (int)tab.size();
+    d.tpp_off = (int)tab.size();
+    d.tpp_total = (int)tab2.size();
+    tab.insert(tab.end(), tab2.begin(), tab2.end());
     cudaFree(ctx->d_tab);
     ctx->d_tab = nullptr;
     if (!tab.empty()) {

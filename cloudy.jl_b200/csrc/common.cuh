@@ -32,7 +32,8 @@ struct DevConfig {
     int bins_per_log_unit;         // MovingThreshold: per-parcel grid density (15 in the reference)
     int n_bins[MAXN], tab_off[MAXN];
     int rec_off[MAXN], rec_near[MAXN], rec_far[MAXN];  // packed node records of the thread-per-parcel kernel (tpp_kernel.cuh)
-    int tab_total;                 // doubles of grid tables to stage in shared memory
+    int tab_total;                 // doubles of SoA grid tables the lane-cooperative kernel stages in shared memory
+    int tpp_off, tpp_total;        // region of `tab` the thread-per-parcel kernel stages (node records, Gauss-Legendre rule)
     int n_vel, nz;
     double c[MAXN][MAXN][MAXP][MAXP];
     double thr[MAXN];

@@ -359,9 +359,9 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
     extern __shared__ double smem[];
     __shared__ TppShared sh;
     double* sTab = smem;
-    double* sCt = smem + ((cfg.tab_total + 1) & ~1);
+    double* sCt = smem + ((cfg.tpp_total + 1) & ~1);
     const int tid = threadIdx.x;
-    for (int i = tid; i < cfg.tab_total; i += TPP_THREADS) sTab[i] = cfg.tab[i];
+    for (int i = tid; i < cfg.tpp_total; i += TPP_THREADS) sTab[i] = cfg.tab[cfg.tpp_off + i];
     for (int i = tid; i < kSerZ * kSerA; i += TPP_THREADS) sh.deg[i / kSerA][i % kSerA] = kSeriesDeg2[i / kSerA][i % kSerA];
     if (tid < kSerA) { sh.cfd[tid] = kCfDepth[tid]; sh.serlim[tid] = kSeriesLimit[tid]; }
     if (tid < 32) sh.exp32[tid] = exp2((double)tid / 32.0);
