@@ -16,5 +16,5 @@ from .kernel_tensors import (CoalescenceTensor, get_normalized_kernel_tensor, ch
                              LongKernelFunction, get_normalized_kernel_func)
 from .coalescence import (CoalescenceData, get_coal_ints, AnalyticalCoalStyle, NumericalCoalStyle, FixedThreshold,
                           MovingThreshold, log_grid, build_config)
-from .sedimentation import get_sedimentation_flux
+from .sedimentation import get_sedimentation_flux, get_cond_evap, get_standard_N_q
 from .ensemble import (ParcelEnsemble, CoalescenceModel, ModelParameters, make_box_model_rhs, make_rainshaft_rhs)

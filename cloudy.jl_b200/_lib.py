@@ -60,6 +60,8 @@ SIGNATURES = {
     "cloudy_ssprk33_steps": (_P, _P, C.c_double, C.c_int32, C.c_int32),
     "cloudy_moment_sums_device": (_P, _P, C.c_void_p),
     "cloudy_moment_sums": (_P, _P, _D),
+    "cloudy_cond_evap": (_P, _P, C.c_double, C.c_void_p, C.c_double, C.c_double, _P),
+    "cloudy_standard_N_q": (_P, _P, C.c_double, C.c_int32, C.c_void_p),
     "cloudy_coal_tendency_host": (_P, _D, _D, C.c_int64),
     "cloudy_error_count": (_P, _I64),
     "cloudy_moment": (_P, C.c_int32, _D, C.c_double, _D),
@@ -67,6 +69,8 @@ SIGNATURES = {
     "cloudy_moment_source_helper": (_P, C.c_int32, _D, C.c_double, C.c_double, C.c_double, C.c_int32, _D),
     "cloudy_get_coal_ints_1": (_P, _D, _D),
     "cloudy_get_sedimentation_flux_1": (_P, C.c_int32, _I32, _D, C.c_int32, _D, _D),
+    "cloudy_get_cond_evap_1": (_P, C.c_int32, _I32, _D, C.c_double, C.c_double, C.c_double, _D),
+    "cloudy_get_standard_N_q_1": (_P, C.c_int32, _I32, _D, C.c_double, _D),
     "cloudy_integrate_simpson": (_P, C.c_int32, C.c_double, _D, _D),
     "cloudy_measure_fp64_peak": (_P, _D),
 }

@@ -709,6 +709,82 @@ __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevCo
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// "next row" kernels: condensation tendency and the cloud/rain split diagnostic (thread per parcel)
+// ------------------------------------------------------------------------------------------------
+struct AuxArgs {
+    const double* u_in;
+    long long s_in, n;
+    double* out;
+    long long s_out;
+    int params_in;     // u_in holds (n, θ|μ[, k|σ]) of ONE set of distributions instead of moments
+    int normalized;    // N_q: rebuild distributions from moments / norms (1) or from the raw moments (0)
+    double s, xi_n, rho_l, cutoff;
+    const double* d_s;  // per-parcel supersaturation (optional)
+};
+
+__device__ inline ModeParams aux_params(const DevConfig& cfg, const AuxArgs& a, int i, long long p, bool normalise) {
+    const int s0 = cfg.slot0[i], np = cfg.nprog[i], kind = cfg.kind[i];
+    double m[3] = {0.0, 0.0, 0.0};
+    for (int q = 0; q < np; ++q) m[q] = a.u_in[(s0 + q) * a.s_in + p];
+    ModeParams mp;
+    if (a.params_in) {
+        mp.n = m[0]; mp.a = m[1]; mp.b = (np > 2) ? m[2] : 1.0; mp.invalid = 0;
+        return mp;
+    }
+    if (normalise)
+        for (int q = 0; q < np; ++q) m[q] /= cfg.norm[s0 + q];
+    return params_from_moments(kind, m[0], m[1], m[2], kind == CLOUDY_GAMMA ? cfg.k_lo : -INFINITY, kind == CLOUDY_GAMMA ? cfg.k_hi : INFINITY);
+}
+
+// get_cond_evap — src/Sources/Condensation.jl:22-37 (normalisation of rhs_condensation!, box_model_helpers.jl:55-67)
+__global__ void __launch_bounds__(256) cond_evap_kernel(const __grid_constant__ DevConfig cfg, const AuxArgs a) {
+    const double geom = pow(4.0 * M_PI / 3.0, 2.0 / 3.0) / pow(a.rho_l, 1.0 / 3.0);
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < a.n; p += (long long)gridDim.x * blockDim.x) {
+        const double s = a.d_s ? a.d_s[p] : a.s;
+        for (int i = 0; i < cfg.N; ++i) {
+            const int s0 = cfg.slot0[i], np = cfg.nprog[i], kind = cfg.kind[i];
+            const ModeParams mp = aux_params(cfg, a, i, p, true);
+            for (int j = 1; j <= np; ++j) {
+                double v = 0.0;
+                if (j >= 2) v = 3 * a.xi_n * s * (j - 1) * moment_real(kind, mp.n, mp.a, mp.b, (double)(j - 1) - 2.0 / 3.0) * geom;
+                a.out[(s0 + j - 1) * a.s_out + p] = a.params_in ? v : v * cfg.norm[s0 + j - 1];
+            }
+        }
+    }
+}
+
+// partial_moment(dist, q, x) — ParticleDistributions.jl:226-285 (Lognormal: the closed form of the reference's quadgk)
+__device__ inline double partial_moment_dev(int kind, double n, double a, double b, double q, double x) {
+    switch (kind) {
+        case CLOUDY_EXPONENTIAL: return n * pow(a, q) * igam_lower(q + 1.0, x / a);
+        case CLOUDY_GAMMA: return n * pow(a, q) * igam_lower(q + b, x / a) / tgamma(b);
+        case CLOUDY_MONODISPERSE: return (x < a) ? 0.0 : n * pow(a, q);
+        default: return n * exp(q * a + q * q * b * b / 2) * norm_cdf((log(x) - a - q * b * b) / b);
+    }
+}
+
+// get_standard_N_q — ParticleDistributions.jl:634-687; out[4][n] = N_liq, N_rai, M_liq, M_rai
+__global__ void __launch_bounds__(256) nq_kernel(const __grid_constant__ DevConfig cfg, const AuxArgs a) {
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < a.n; p += (long long)gridDim.x * blockDim.x) {
+        double nl = 0.0, nr = 0.0, ml = 0.0, mr = 0.0;
+        for (int i = 0; i < cfg.N; ++i) {
+            const int kind = cfg.kind[i];
+            const ModeParams mp = aux_params(cfg, a, i, p, a.normalized != 0);
+            const double p0 = partial_moment_dev(kind, mp.n, mp.a, mp.b, 0.0, a.cutoff);
+            const double p1 = partial_moment_dev(kind, mp.n, mp.a, mp.b, 1.0, a.cutoff);
+            nl += p0;
+            ml += p1;
+            nr += moment_real(kind, mp.n, mp.a, mp.b, 0.0) - p0;
+            mr += moment_real(kind, mp.n, mp.a, mp.b, 1.0) - p1;
+        }
+        a.out[0 * a.s_out + p] = nl;
+        a.out[1 * a.s_out + p] = nr;
+        a.out[2 * a.s_out + p] = ml;
+        a.out[3 * a.s_out + p] = mr;
+    }
+}
+
 // FP64 peak: independent FMA chains
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -1605,6 +1681,81 @@ int cloudy_get_coal_ints_1(cloudy_ctx* ctx, const double* params, double* out) {
     a.params_in = 1;
     if ((rc = launch_rhs(ctx, CLOUDY_MODEL_BOX, a))) return rc;
     return cloudy_state_download(ctx, ctx->tmp[1], out, 1);
+}
+
+// ---- condensation and diagnostics ("next" rows) ---------------------------------------------------
+static int launch_aux(cloudy_ctx* ctx, const void* fn, const AuxArgs& a) {
+    long long blocks = std::min<long long>((a.n + 255) / 256, (long long)ctx->sm_count * 8);
+    void* params[2] = {(void*)&ctx->dev, (void*)&a};
+    CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)std::max<long long>(blocks, 1)), dim3(256), params, 0, ctx->stream));
+    ctx->launches++;
+    return CLOUDY_OK;
+}
+
+int cloudy_cond_evap(cloudy_ctx* ctx, const cloudy_state* m, double s, const double* d_s, double xi, double rho_l, cloudy_state* dm) {
+    int rc = check_pair(ctx, m, dm);
+    if (rc) return rc;
+    if (m->n == 0) return CLOUDY_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    AuxArgs a;
+    memset(&a, 0, sizeof(a));
+    a.u_in = m->d; a.s_in = m->stride; a.n = m->n; a.out = dm->d; a.s_out = dm->stride;
+    a.s = s; a.d_s = d_s; a.rho_l = rho_l;
+    a.xi_n = xi / pow(ctx->cfg.norms[1], 2.0 / 3.0);  // box_model_helpers.jl:65
+    return launch_aux(ctx, (const void*)cond_evap_kernel, a);
+}
+
+int cloudy_standard_N_q(cloudy_ctx* ctx, const cloudy_state* m, double size_cutoff, int32_t normalized, double* d_out) {
+    if (!ctx || !m || !d_out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (!ctx->configured) return fail(CLOUDY_ERR_STATE, "cloudy_config_set has not been called");
+    if (m->n == 0) return CLOUDY_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    AuxArgs a;
+    memset(&a, 0, sizeof(a));
+    a.u_in = m->d; a.s_in = m->stride; a.n = m->n; a.out = d_out; a.s_out = m->n;
+    a.cutoff = size_cutoff; a.normalized = normalized;
+    return launch_aux(ctx, (const void*)nq_kernel, a);
+}
+
+// one set of distributions given by parameters: a private one-parcel configuration (kinds only matter)
+static int aux_single(cloudy_ctx* ctx, int32_t n_modes, const int32_t* kinds, const double* params, bool nq, double s, double xi,
+                      double rho_l, double cutoff, double* out) {
+    if (!ctx || !kinds || !params || !out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (n_modes < 1 || n_modes > MAXN) return fail(CLOUDY_ERR_ARG, "n_modes must be 1..4");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    DevConfig d;
+    memset((void*)&d, 0, sizeof(d));
+    d.N = n_modes;
+    double h[MAXSLOT + 4];
+    int slot = 0;
+    for (int i = 0; i < n_modes; ++i) {
+        if (kinds[i] < 0 || kinds[i] > 3) return fail(CLOUDY_ERR_ARG, "unknown distribution kind");
+        d.kind[i] = kinds[i]; d.nprog[i] = kind_nparams(kinds[i]); d.slot0[i] = slot;
+        for (int q = 0; q < d.nprog[i]; ++q) { d.norm[slot] = 1.0; h[slot++] = params[3 * i + q]; }
+    }
+    d.nslots = slot;
+    double* dbuf = ctx->d_scratch;  // [0..slot) in, [16..) out
+    CUDA_TRY(cudaMemcpyAsync(dbuf, h, sizeof(double) * slot, cudaMemcpyHostToDevice, ctx->stream));
+    AuxArgs a;
+    memset(&a, 0, sizeof(a));
+    a.u_in = dbuf; a.s_in = 1; a.n = 1; a.out = dbuf + 16; a.s_out = 1; a.params_in = 1;
+    a.s = s; a.xi_n = xi; a.rho_l = rho_l; a.cutoff = cutoff;
+    void* kp[2] = {(void*)&d, (void*)&a};
+    CUDA_TRY(cudaLaunchKernel(nq ? (const void*)nq_kernel : (const void*)cond_evap_kernel, dim3(1), dim3(32), kp, 0, ctx->stream));
+    ctx->launches++;
+    CUDA_TRY(cudaMemcpyAsync(out, dbuf + 16, sizeof(double) * (nq ? 4 : slot), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return CLOUDY_OK;
+}
+
+int cloudy_get_cond_evap_1(cloudy_ctx* ctx, int32_t n_modes, const int32_t* kinds, const double* params, double s, double xi, double rho_l,
+                           double* out) {
+    return aux_single(ctx, n_modes, kinds, params, false, s, xi, rho_l, 0.0, out);
+}
+
+int cloudy_get_standard_N_q_1(cloudy_ctx* ctx, int32_t n_modes, const int32_t* kinds, const double* params, double size_cutoff,
+                              double* out) {
+    return aux_single(ctx, n_modes, kinds, params, true, 0.0, 0.0, 1000.0, size_cutoff, out);
 }
 
 int cloudy_measure_fp64_peak(cloudy_ctx* ctx, double* tflops) {

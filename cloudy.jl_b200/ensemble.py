@@ -66,6 +66,38 @@ class ParcelEnsemble:
             pass
 
 
+class _DeviceBuffer:
+    """Plain device scratch (n doubles) borrowed from a one-slot... implemented with cudart through ctypes."""
+
+    _rt = None
+
+    def __init__(self, ctx, n):
+        if _DeviceBuffer._rt is None:
+            import ctypes.util
+            import glob
+            cands = glob.glob("/usr/local/cuda/lib64/libcudart.so*") + [ctypes.util.find_library("cudart") or "libcudart.so"]
+            _DeviceBuffer._rt = C.CDLL(cands[0])
+        self.ctx = ctx
+        self.n = int(n)
+        p = C.c_void_p()
+        rc = _DeviceBuffer._rt.cudaMalloc(C.byref(p), C.c_size_t(8 * max(self.n, 1)))
+        if rc != 0:
+            raise L.CloudyError(-2, f"cudaMalloc failed ({rc})")
+        self.ptr = p.value
+
+    def download(self, out):
+        self.ctx.sync()
+        rc = _DeviceBuffer._rt.cudaMemcpy(out.ctypes.data_as(C.c_void_p), C.c_void_p(self.ptr), C.c_size_t(8 * self.n), C.c_int(2))
+        if rc != 0:
+            raise L.CloudyError(-2, f"cudaMemcpy failed ({rc})")
+
+    def __del__(self):
+        try:
+            _DeviceBuffer._rt.cudaFree(C.c_void_p(self.ptr))
+        except Exception:
+            pass
+
+
 class CoalescenceModel:
     """Run-constant configuration on a device context + the batched operators."""
 
@@ -106,6 +138,21 @@ class CoalescenceModel:
     def ssprk33_steps(self, u: ParcelEnsemble, dt: float, n_steps: int, model: int = L.MODEL_BOX):
         self.activate()
         L.check(L.load().cloudy_ssprk33_steps(self.ctx.handle, u.handle, float(dt), int(n_steps), int(model)))
+
+    def cond_evap(self, m: ParcelEnsemble, dm: ParcelEnsemble, s: float, ξ: float, ρ_l: float = 1000.0, d_s_ptr: int = 0):
+        """rhs_condensation! for every parcel (box_model_helpers.jl:55-67); ``d_s_ptr``: optional device array of per-parcel s."""
+        self.activate()
+        L.check(L.load().cloudy_cond_evap(self.ctx.handle, m.handle, float(s), C.c_void_p(d_s_ptr) if d_s_ptr else None, float(ξ),
+                                          float(ρ_l), dm.handle))
+
+    def standard_N_q(self, m: ParcelEnsemble, size_cutoff: float, normalized: bool = False):
+        """get_standard_N_q for every parcel → (4, n) array (N_liq, N_rai, M_liq, M_rai), cf. netcdf_helpers.jl:106-121."""
+        self.activate()
+        out = np.zeros((4, m.n))
+        buf = _DeviceBuffer(self.ctx, 4 * m.n)
+        L.check(L.load().cloudy_standard_N_q(self.ctx.handle, m.handle, float(size_cutoff), int(bool(normalized)), C.c_void_p(buf.ptr)))
+        buf.download(out)
+        return out
 
     def moment_sums(self, u: ParcelEnsemble):
         out = np.zeros(self.n_slots)

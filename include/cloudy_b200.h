@@ -128,6 +128,15 @@ int cloudy_ssprk33_steps(cloudy_ctx* ctx, cloudy_state* u, double dt, int32_t n_
  * can all-reduce it with NCCL without a host round trip). */
 int cloudy_moment_sums_device(cloudy_ctx* ctx, const cloudy_state* u, double* d_out);
 int cloudy_moment_sums(cloudy_ctx* ctx, const cloudy_state* u, double* host_out);
+/* dm = rhs_condensation!(dm, m, p, s): get_cond_evap(pdists(m), s, xi / norms[2]^(2/3), rho_l) .* mom_norms for every parcel.
+ * test/examples/utils/box_model_helpers.jl:55-67 → src/Sources/Condensation.jl:22-37.  d_s: optional DEVICE array of
+ * per-parcel supersaturations (NULL → the scalar s for all parcels). */
+int cloudy_cond_evap(cloudy_ctx* ctx, const cloudy_state* m, double s, const double* d_s, double xi, double rho_l, cloudy_state* dm);
+/* (N_liq, N_rai, M_liq, M_rai) = get_standard_N_q(pdists(m), size_cutoff) for every parcel/cell
+ * (src/ParticleDistributions/ParticleDistributions.jl:634-687; caller: test/examples/utils/netcdf_helpers.jl:106-121).
+ * normalized = 0: distributions are rebuilt from the RAW moments like netcdf_helpers.jl does; 1: from moments / norms.
+ * d_out: DEVICE pointer to 4*n doubles, quantity-major ([4][n]). */
+int cloudy_standard_N_q(cloudy_ctx* ctx, const cloudy_state* m, double size_cutoff, int32_t normalized, double* d_out);
 /* convenience: host moments in, host tendencies out (upload + kernel + download, chunked & overlapped) */
 int cloudy_coal_tendency_host(cloudy_ctx* ctx, const double* host_m, double* host_dm, int64_t n_parcels);
 /* number of parcels whose moments were invalid for their distribution (Lognormal sqrt(log(.)<0),
@@ -154,6 +163,13 @@ int cloudy_get_coal_ints_1(cloudy_ctx* ctx, const double* params, double* out);
 /* get_sedimentation_flux(pdists, vel) for ONE set of distributions, vel given explicitly. Sedimentation.jl:22-37 */
 int cloudy_get_sedimentation_flux_1(cloudy_ctx* ctx, int32_t n_modes, const int32_t* kinds, const double* params,
                                     int32_t n_vel, const double* vel, double* out);
+/* get_cond_evap(pdists, s, xi, rho_l) for ONE set of distributions (kinds/params as above). Condensation.jl:22-37 */
+int cloudy_get_cond_evap_1(cloudy_ctx* ctx, int32_t n_modes, const int32_t* kinds, const double* params, double s, double xi,
+                           double rho_l, double* out);
+/* get_standard_N_q(pdists, size_cutoff) for ONE set of distributions; out = (N_liq, N_rai, M_liq, M_rai).
+ * ParticleDistributions.jl:634-687 */
+int cloudy_get_standard_N_q_1(cloudy_ctx* ctx, int32_t n_modes, const int32_t* kinds, const double* params, double size_cutoff,
+                              double* out);
 /* integrate_SimpsonEvenFast(n_bins, dx, y) with tabulated y[1..n_bins+1] — ParticleDistributions.jl:698-710 */
 int cloudy_integrate_simpson(cloudy_ctx* ctx, int32_t n_bins, double dx, const double* y, double* out);
 

@@ -535,6 +535,36 @@ def get_cond_evap(pdists: Sequence[Dist], s: float, xi: float, rho_l: float = 10
     return np.array(out)
 
 
+def rhs_condensation(mom: Sequence[float], par: "ModelParams", s: float, xi: float):
+    """rhs_condensation! — test/examples/utils/box_model_helpers.jl:55-67."""
+    pd, _, mom_norms = dists_from_state(mom, par)
+    xi_n = xi / par.norms[1] ** (2 / 3)
+    return get_cond_evap(pd, s, xi_n) * np.array(mom_norms)
+
+
+# --------------------------------------------------------------------------------------
+# Diagnostics — ParticleDistributions.jl:226-285, :634-687
+# --------------------------------------------------------------------------------------
+def partial_moment(d: Dist, q: float, x_threshold: float) -> float:
+    if d.kind == EXPONENTIAL:
+        return d.n * d.p1 ** q * float(sp.gammainc(q + 1.0, x_threshold / d.p1)) * float(sp.gamma(q + 1.0))
+    if d.kind == GAMMA:
+        return d.n * d.p1 ** q * float(sp.gammainc(q + d.p2, x_threshold / d.p1)) * float(sp.gamma(q + d.p2)) / float(sp.gamma(d.p2))
+    if d.kind == MONODISPERSE:
+        return 0.0 if x_threshold < d.p1 else d.n * d.p1 ** q
+    # Lognormal: quadgk(x -> x^q * dist(x), 0, x_threshold) (:261-269)
+    return spint.quad(lambda x: x ** q * float(_lognormal_density_vec(d, x)), 0.0, x_threshold, epsabs=0.0, epsrel=math.sqrt(EPS), limit=200)[0]
+
+
+def get_standard_N_q(pdists: Sequence[Dist], size_cutoff: float = 1e-6):
+    """(N_liq, N_rai, M_liq, M_rai) — ParticleDistributions.jl:634-687."""
+    N_liq = sum(partial_moment(d, 0.0, size_cutoff) for d in pdists)
+    M_liq = sum(partial_moment(d, 1.0, size_cutoff) for d in pdists)
+    N_rai = sum(moment(d, 0.0) - partial_moment(d, 0.0, size_cutoff) for d in pdists)
+    M_rai = sum(moment(d, 1.0) - partial_moment(d, 1.0, size_cutoff) for d in pdists)
+    return N_liq, N_rai, M_liq, M_rai
+
+
 # --------------------------------------------------------------------------------------
 # RHS glue — test/examples/utils/box_model_helpers.jl:29-53, rainshaft_helpers.jl:45-88
 # --------------------------------------------------------------------------------------

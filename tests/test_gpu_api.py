@@ -166,3 +166,39 @@ def test_error_behaviour(cb):
         cb.get_moments_normalizing_factors((2, 2), (0.0, 1.0))  # norms must be positive!
     with pytest.raises(Exception):
         cb.get_dist_moment_ind((2, 2, 3), 4, 2)
+
+
+def test_condensation_golden(cb):
+    """test_Sources_correctness.jl:274-312"""
+    Exp, Gam = cb.ExponentialPrimitiveParticleDistribution, cb.GammaPrimitiveParticleDistribution
+    ξ, s = 1e-6, 0.01
+    geom = (4 * math.pi / 3) ** (2 / 3) / 1000.0 ** (1 / 3)
+    pd = (Exp(1.0, 1.0),)
+    got = cb.get_cond_evap(pd, s, ξ)
+    assert got[0] == 0.0 and approx(got[1], 3 * ξ * s * cb.moment(pd[0], 1 - 2 / 3) * geom, 1e-13)
+    pd = (Exp(1.0, 1.0), Gam(1.0, 2.0, 3.0), Gam(0.1, 10.0, 3.0))
+    got = cb.get_cond_evap(pd, s, ξ)
+    want = (0.0, 3 * ξ * s * cb.moment(pd[0], 1 - 2 / 3) * geom,
+            0.0, 3 * ξ * s * cb.moment(pd[1], 1 - 2 / 3) * geom, 3 * 2 * ξ * s * cb.moment(pd[1], 2 - 2 / 3) * geom,
+            0.0, 3 * ξ * s * cb.moment(pd[2], 1 - 2 / 3) * geom, 3 * 2 * ξ * s * cb.moment(pd[2], 2 - 2 / 3) * geom)
+    assert np.allclose(got, want, rtol=1e-13, atol=0)
+
+
+def test_get_standard_N_q(cb):
+    """test_ParticleDistributions_correctness.jl:234-247"""
+    from oracle import cloudy_oracle as O
+    Exp, Gam, Mono, LogN = (cb.ExponentialPrimitiveParticleDistribution, cb.GammaPrimitiveParticleDistribution,
+                            cb.MonodispersePrimitiveParticleDistribution, cb.LognormalPrimitiveParticleDistribution)
+    pd = (Exp(10.0, 1.0), Gam(5.0, 10.0, 2.0))
+    q1 = cb.get_standard_N_q(pd, 1.0)
+    q2 = cb.get_standard_N_q(pd, 0.5)
+    for q in (q1, q2):
+        assert approx(q.N_liq + q.N_rai, 15.0) and approx(q.M_liq + q.M_rai, 110.0)
+    assert q1.N_liq > q2.N_liq and q1.M_liq > q2.M_liq
+    ref = O.get_standard_N_q((O.Exponential(10.0, 1.0), O.Gamma(5.0, 10.0, 2.0)), 1.0)
+    assert np.allclose((q1.N_liq, q1.N_rai, q1.M_liq, q1.M_rai), ref, rtol=1e-13)
+    # the performance-test tuple (performance_tests.jl:94-100): Monodisperse, Lognormal, Gamma
+    pd = (Mono(1.0, 0.5), LogN(1.0, 0.5, 2.0), Gam(5.0, 10.0, 2.0))
+    q = cb.get_standard_N_q(pd, 1.2)
+    ref = O.get_standard_N_q((O.Monodisperse(1.0, 0.5), O.Lognormal(1.0, 0.5, 2.0), O.Gamma(5.0, 10.0, 2.0)), 1.2)
+    assert np.allclose((q.N_liq, q.N_rai, q.M_liq, q.M_rai), ref, rtol=1e-7)  # Lognormal: the reference integrates adaptively at sqrt(eps)

@@ -259,3 +259,35 @@ def test_lognormal_mode_with_threshold(cb):
         assert ok, (i, worst)
     # mass is conserved whatever the quadrature
     assert np.all(np.abs(got[:, 1] + got[:, 4]) <= 1e-12 * (np.abs(got[:, 1]) + np.abs(got[:, 4]) + 1e-300))
+
+
+def test_condensation_batched(cb):
+    """rhs_condensation! (box_model_helpers.jl:55-67) over an ensemble, scalar and per-parcel supersaturation"""
+    from cloudy_b200 import workloads as W
+    par, state = W.c2_gamma_gamma(n_parcels=300)
+    opar = oracle_params(par)
+    model = cb.CoalescenceModel(par)
+    u = model.ensemble(state.shape[0]).upload(state)
+    du = model.ensemble(state.shape[0])
+    s, xi = 0.01, 1e-6
+    model.cond_evap(u, du, s, xi)
+    got = du.download()
+    for i in range(0, 300, 7):
+        ref = O.rhs_condensation(state[i], opar, s, xi)
+        assert np.allclose(got[i], ref, rtol=1e-12, atol=0), (i, got[i], ref)
+
+
+def test_standard_N_q_batched(cb):
+    """cloud/rain split of every cell as rainshaft_output computes it (netcdf_helpers.jl:106-121: raw moments, cutoff 5.236e-10)"""
+    from cloudy_b200 import workloads as W
+    par, cols = W.c3_rainshaft(n_columns=2, nz=20)
+    st = _rain_state(cols, seed=11).reshape(-1, 6)
+    st[st < 0] = 0
+    model = cb.CoalescenceModel(par, nz=20)
+    u = model.ensemble(st.shape[0]).upload(st)
+    got = model.standard_N_q(u, 5.236e-10, normalized=False)
+    for i in range(st.shape[0]):
+        pd = [O.update_dist_from_moments(O.Dist(O.GAMMA, 0.0, 1.0, 1.0), st[i, 3 * j:3 * j + 3]) for j in range(2)]
+        ref = np.array(O.get_standard_N_q(pd, 5.236e-10))
+        scale = max(st[i, 0] + st[i, 3], 1e-300), max(st[i, 0] + st[i, 3], 1e-300), max(st[i, 1] + st[i, 4], 1e-300), max(st[i, 1] + st[i, 4], 1e-300)
+        assert np.all(np.abs(got[:, i] - ref) <= 1e-12 * np.array(scale)), (i, got[:, i], ref)

@@ -14,7 +14,7 @@ def test_library_exports_every_declared_symbol():
     import cloudy_b200
     from cloudy_b200 import _lib
     header = open(os.path.join(ROOT, "include", "cloudy_b200.h")).read()
-    declared = set(re.findall(r"\b(cloudy_[a-z0-9_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(cloudy_[A-Za-z0-9_]+)\s*\(", header))
     declared -= {"cloudy_ctx", "cloudy_state", "cloudy_config"}
     lib = _lib.load()
     for name in sorted(declared):
