@@ -48,6 +48,7 @@ SIGNATURES = {
     "cloudy_sync": (_P,),
     "cloudy_launch_count": (_P, _I64),
     "cloudy_set_lanes": (_P, C.c_int),
+    "cloudy_set_regime_sort": (_P, C.c_int),
     "cloudy_state_create": (_P, C.c_int64, C.POINTER(_P)),
     "cloudy_state_destroy": (_P,),
     "cloudy_state_upload": (_P, _P, _D, C.c_int64),

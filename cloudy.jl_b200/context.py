@@ -37,6 +37,9 @@ class Context:
     def set_lanes(self, lanes: int):
         L.check(self._lib.cloudy_set_lanes(self.handle, int(lanes)))
 
+    def set_regime_sort(self, on: bool):
+        L.check(self._lib.cloudy_set_regime_sort(self.handle, int(bool(on))))
+
     def launch_count(self) -> int:
         v = C.c_int64()
         L.check(self._lib.cloudy_launch_count(self.handle, C.byref(v)))

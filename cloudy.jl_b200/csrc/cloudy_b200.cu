@@ -785,6 +785,78 @@ __global__ void __launch_bounds__(256) nq_kernel(const __grid_constant__ DevConf
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// regime sort (optional): order the parcels so that the 32 parcels of a warp need a similar series length and
+// the same series / continued-fraction regime.  Purely a performance hint — a parcel's result does not depend on
+// its position — so the order may be reused across the stages of a time step.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) regime_key_kernel(const __grid_constant__ DevConfig cfg, const KArgs args, unsigned char* __restrict__ keys,
+                                                         unsigned int* __restrict__ hist) {
+    __shared__ unsigned int sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p < args.n) {
+        unsigned int key = 0;
+        int used = 0;
+        for (int i = 0; i < cfg.N - 1 && used < 2; ++i) {
+            if (!cfg.quad[i]) continue;
+            const int s0 = cfg.slot0[i], np = cfg.nprog[i], kind = cfg.kind[i];
+            double m[3] = {0.0, 0.0, 0.0};
+            for (int q = 0; q < np; ++q) m[q] = args.u_in[(s0 + q) * args.s_in + p * args.ps_in] / cfg.norm[s0 + q];
+            const ModeParams mp = params_from_moments(kind, m[0], m[1], m[2], kind == CLOUDY_GAMMA ? cfg.k_lo : -INFINITY,
+                                                      kind == CLOUDY_GAMMA ? cfg.k_hi : INFINITY);
+            unsigned int sub = 0;
+            if (mp.n != 0.0) {
+                const double a_top = mp.b + (double)(cfg.Mp[i] - 1);
+                const int ai = series_a_bin(a_top);
+                const double ser_lim = kSeriesLimit[ai];
+                const double X = cfg.thr[i] / mp.a;
+                const int zi = series_z_bin(fmin(X, ser_lim - 0.5));
+                const unsigned int deg = kSeriesDeg2[zi][ai];
+                sub = (X >= ser_lim ? 1u : 0u) | (((deg >> 3) & 7u) << 1);
+                sub = sub == 0 ? 2u : sub;  // keep 0 for "empty mode"
+            }
+            key |= sub << (4 * used);
+            ++used;
+        }
+        keys[p] = (unsigned char)key;
+        atomicAdd(&sh[key], 1u);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) regime_scan_kernel(const unsigned int* __restrict__ hist, unsigned int* __restrict__ cursor) {
+    __shared__ unsigned int sh[256];
+    sh[threadIdx.x] = hist[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int run = 0;
+        for (int i = 0; i < 256; ++i) { const unsigned int c = sh[i]; sh[i] = run; run += c; }
+    }
+    __syncthreads();
+    cursor[threadIdx.x] = sh[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) regime_scatter_kernel(const unsigned char* __restrict__ keys, unsigned int* __restrict__ cursor,
+                                                             int* __restrict__ perm, long long n) {
+    __shared__ unsigned int cnt[256];
+    __shared__ unsigned int base[256];
+    cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    unsigned int key = 0, rank = 0;
+    if (p < n) {
+        key = keys[p];
+        rank = atomicAdd(&cnt[key], 1u);
+    }
+    __syncthreads();
+    if (cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], cnt[threadIdx.x]);
+    __syncthreads();
+    if (p < n) perm[base[key] + rank] = (int)p;
+}
+
 // FP64 peak: independent FMA chains
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -837,6 +909,12 @@ struct cloudy_ctx {
     double* d_scratch;     // small device scratch for scalar entry points
     cloudy_state* tmp[3];  // stepper / host-path work buffers
     cloudy_state* flux;    // rainshaft: per-cell sedimentation flux for the thread-per-parcel kernel
+    int sort_mode;         // regime sort of the parcel order before the thread-per-parcel kernel (0 off, 1 on)
+    unsigned char* d_keys;
+    int* d_perm;
+    unsigned int* d_hist;  // [0..256) histogram, [256..512) cursors
+    long long sort_cap;
+    bool perm_valid;       // d_perm holds an order for the current ensemble size (reused across the stages of a step)
     double* d_stage_aos;   // staging for upload/download
     // host-buffer pipeline (cloudy_coal_tendency_host): chunked H2D / kernel / D2H on three streams
     cudaStream_t s_h2d, s_d2h;
@@ -915,6 +993,32 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
         if ((rc = launch_flux(ctx, fa))) return rc;
         args.flux = ctx->flux->d;
         args.s_flux = ctx->flux->stride;
+    }
+    bool any_quad = false;
+    for (int i = 0; i < d.N - 1; ++i) any_quad = any_quad || d.quad[i];
+    if (ctx->sort_mode && any_quad && !args.params_in && d.thr_style == CLOUDY_FIXED_THRESHOLD && args.n >= 4096 && args.n < (1LL << 31)) {
+        if (ctx->sort_cap < args.n) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(ctx->d_keys); cudaFree(ctx->d_perm);
+            ctx->d_keys = nullptr; ctx->d_perm = nullptr; ctx->sort_cap = 0;
+            CUDA_TRY(cudaMalloc(&ctx->d_keys, (size_t)args.n));
+            CUDA_TRY(cudaMalloc(&ctx->d_perm, sizeof(int) * (size_t)args.n));
+            if (!ctx->d_hist) CUDA_TRY(cudaMalloc(&ctx->d_hist, sizeof(unsigned int) * 512));
+            ctx->sort_cap = args.n;
+            ctx->perm_valid = false;
+        }
+        if (!ctx->perm_valid) {
+            CUDA_TRY(cudaMemsetAsync(ctx->d_hist, 0, sizeof(unsigned int) * 512, ctx->stream));
+            const unsigned blocks = (unsigned)((args.n + 255) / 256);
+            void* kp[4] = {(void*)&ctx->dev, (void*)&args, (void*)&ctx->d_keys, (void*)&ctx->d_hist};
+            CUDA_TRY(cudaLaunchKernel((const void*)regime_key_kernel, dim3(blocks), dim3(256), kp, 0, ctx->stream));
+            unsigned int* cursor = ctx->d_hist + 256;
+            regime_scan_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_hist, cursor);
+            regime_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_keys, cursor, ctx->d_perm, args.n);
+            CUDA_TRY(cudaGetLastError());
+            ctx->launches += 3;
+        }
+        args.perm = ctx->d_perm;
     }
     size_t smem = sizeof(double) * (((size_t)d.tpp_total + 1) / 2 * 2 + (size_t)TPP_CT_ROWS * TPP_THREADS);
     CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -999,6 +1103,9 @@ int cloudy_ctx_destroy(cloudy_ctx* ctx) {
     for (int i = 0; i < 3; ++i)
         if (ctx->tmp[i]) cloudy_state_destroy(ctx->tmp[i]);
     if (ctx->flux) cloudy_state_destroy(ctx->flux);
+    cudaFree(ctx->d_keys);
+    cudaFree(ctx->d_perm);
+    cudaFree(ctx->d_hist);
     cudaFree(ctx->d_tab);
     cudaFree(ctx->d_err);
     cudaFree(ctx->d_partial);
@@ -1025,6 +1132,13 @@ int cloudy_set_lanes(cloudy_ctx* ctx, int lanes) {
     if (lanes != 0 && lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32)
         return fail(CLOUDY_ERR_ARG, "lanes must be 0 (auto), 1 (thread per parcel), 4, 8, 16 or 32");
     ctx->lanes = lanes;
+    return CLOUDY_OK;
+}
+
+int cloudy_set_regime_sort(cloudy_ctx* ctx, int on) {
+    if (!ctx) return fail(CLOUDY_ERR_ARG, "ctx is NULL");
+    ctx->sort_mode = on ? 1 : 0;
+    ctx->perm_valid = false;
     return CLOUDY_OK;
 }
 
@@ -1425,7 +1539,9 @@ int cloudy_ssprk33_steps(cloudy_ctx* ctx, cloudy_state* u, double dt, int32_t n_
         a.ps_in = a.ps_out = 1;
         // stage 1: tmp = u + dt f(u)
         a.u_in = cur; a.u_n = nullptr; a.out = t1; a.cn = 0; a.ci = 1; a.cf = 1; a.div = 1;
+        ctx->perm_valid = false;  // new regime sort (if enabled) at the first stage, reused by stages 2 and 3
         if ((rc = launch_rhs(ctx, model, a))) return rc;
+        ctx->perm_valid = ctx->sort_mode != 0 && ctx->d_perm != nullptr && ctx->sort_cap >= u->n;
         // stage 2: tmp = (3u + tmp + dt f(tmp))/4
         a.u_in = t1; a.u_n = cur; a.out = t2; a.cn = 3; a.ci = 1; a.cf = 1; a.div = 4;
         if ((rc = launch_rhs(ctx, model, a))) return rc;
@@ -1434,6 +1550,7 @@ int cloudy_ssprk33_steps(cloudy_ctx* ctx, cloudy_state* u, double dt, int32_t n_
         if ((rc = launch_rhs(ctx, model, a))) return rc;
         std::swap(cur, nxt);
     }
+    ctx->perm_valid = false;
     if (cur != u->d) {
         // odd number of swaps: `cur` is a work buffer; hand its storage to the caller's state
         std::swap(u->d, ctx->tmp[2]->d);

@@ -99,6 +99,10 @@ int cloudy_launch_count(cloudy_ctx* ctx, int64_t* out);
 /* execution-shape knob: 0 = auto (thread-per-parcel kernel when the (n_modes, P) shape has an instance, else 8 lanes),
  * 1 = thread per parcel, 4/8/16/32 = that many lanes cooperating on one parcel's quadrature nodes */
 int cloudy_set_lanes(cloudy_ctx* ctx, int lanes);
+/* regime sort (off by default): before the thread-per-parcel kernel, order the parcels by series length and
+ * series / continued-fraction regime so that warps are homogeneous.  Results are bit-identical either way; it pays when
+ * thresholds sit far in the tail for part of the ensemble (continued-fraction regime mixed into every warp). */
+int cloudy_set_regime_sort(cloudy_ctx* ctx, int on);
 
 /* ---- device state ---------------------------------------------------------------------------- */
 int cloudy_state_create(cloudy_ctx* ctx, int64_t n_parcels, cloudy_state** out);
