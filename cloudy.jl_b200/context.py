@@ -37,8 +37,9 @@ class Context:
     def set_lanes(self, lanes: int):
         L.check(self._lib.cloudy_set_lanes(self.handle, int(lanes)))
 
-    def set_regime_sort(self, on: bool):
-        L.check(self._lib.cloudy_set_regime_sort(self.handle, int(bool(on))))
+    def set_regime_sort(self, mode):
+        """0/False off, 1/True always, 2 auto (default)"""
+        L.check(self._lib.cloudy_set_regime_sort(self.handle, int(mode)))
 
     def launch_count(self) -> int:
         v = C.c_int64()

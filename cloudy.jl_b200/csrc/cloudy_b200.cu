@@ -914,7 +914,9 @@ struct cloudy_ctx {
     int* d_perm;
     unsigned int* d_hist;  // [0..256) histogram, [256..512) cursors
     long long sort_cap;
-    bool perm_valid;       // d_perm holds an order for the current ensemble size (reused across the stages of a step)
+    bool perm_valid;       // d_perm may be reused (set by the stepper for stages 2 and 3 of a step)
+    bool perm_fresh;       // a sort ran since the stepper last cleared this flag
+    long long perm_n;      // ensemble size d_perm was computed for
     double* d_stage_aos;   // staging for upload/download
     // host-buffer pipeline (cloudy_coal_tendency_host): chunked H2D / kernel / D2H on three streams
     cudaStream_t s_h2d, s_d2h;
@@ -996,7 +998,8 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
     }
     bool any_quad = false;
     for (int i = 0; i < d.N - 1; ++i) any_quad = any_quad || d.quad[i];
-    if (ctx->sort_mode && any_quad && !args.params_in && d.thr_style == CLOUDY_FIXED_THRESHOLD && args.n >= 4096 && args.n < (1LL << 31)) {
+    const bool want_sort = ctx->sort_mode == 1 || (ctx->sort_mode == 2 && args.n >= 262144);  // auto: pays from ~2e5 parcels (measured)
+    if (want_sort && any_quad && !args.params_in && d.thr_style == CLOUDY_FIXED_THRESHOLD && args.n >= 4096 && args.n < (1LL << 31)) {
         if (ctx->sort_cap < args.n) {
             cudaStreamSynchronize(ctx->stream);
             cudaFree(ctx->d_keys); cudaFree(ctx->d_perm);
@@ -1007,7 +1010,7 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
             ctx->sort_cap = args.n;
             ctx->perm_valid = false;
         }
-        if (!ctx->perm_valid) {
+        if (!ctx->perm_valid || ctx->perm_n != args.n) {
             CUDA_TRY(cudaMemsetAsync(ctx->d_hist, 0, sizeof(unsigned int) * 512, ctx->stream));
             const unsigned blocks = (unsigned)((args.n + 255) / 256);
             void* kp[4] = {(void*)&ctx->dev, (void*)&args, (void*)&ctx->d_keys, (void*)&ctx->d_hist};
@@ -1017,6 +1020,8 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
             regime_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_keys, cursor, ctx->d_perm, args.n);
             CUDA_TRY(cudaGetLastError());
             ctx->launches += 3;
+            ctx->perm_fresh = true;
+            ctx->perm_n = args.n;
         }
         args.perm = ctx->d_perm;
     }
@@ -1087,6 +1092,7 @@ int cloudy_ctx_create(int device, void* stream, cloudy_ctx** out) {
         c->own_stream = true;
     }
     c->lanes = 0;
+    c->sort_mode = 2;
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaMalloc(&c->d_err, sizeof(unsigned long long)));
     CUDA_TRY(cudaMemset(c->d_err, 0, sizeof(unsigned long long)));
@@ -1137,7 +1143,8 @@ int cloudy_set_lanes(cloudy_ctx* ctx, int lanes) {
 
 int cloudy_set_regime_sort(cloudy_ctx* ctx, int on) {
     if (!ctx) return fail(CLOUDY_ERR_ARG, "ctx is NULL");
-    ctx->sort_mode = on ? 1 : 0;
+    if (on < 0 || on > 2) return fail(CLOUDY_ERR_ARG, "regime sort mode must be 0 (off), 1 (on) or 2 (auto)");
+    ctx->sort_mode = on;
     ctx->perm_valid = false;
     return CLOUDY_OK;
 }
@@ -1540,8 +1547,9 @@ int cloudy_ssprk33_steps(cloudy_ctx* ctx, cloudy_state* u, double dt, int32_t n_
         // stage 1: tmp = u + dt f(u)
         a.u_in = cur; a.u_n = nullptr; a.out = t1; a.cn = 0; a.ci = 1; a.cf = 1; a.div = 1;
         ctx->perm_valid = false;  // new regime sort (if enabled) at the first stage, reused by stages 2 and 3
+        ctx->perm_fresh = false;
         if ((rc = launch_rhs(ctx, model, a))) return rc;
-        ctx->perm_valid = ctx->sort_mode != 0 && ctx->d_perm != nullptr && ctx->sort_cap >= u->n;
+        ctx->perm_valid = ctx->perm_fresh;
         // stage 2: tmp = (3u + tmp + dt f(tmp))/4
         a.u_in = t1; a.u_n = cur; a.out = t2; a.cn = 3; a.ci = 1; a.cf = 1; a.div = 4;
         if ((rc = launch_rhs(ctx, model, a))) return rc;

@@ -99,9 +99,9 @@ int cloudy_launch_count(cloudy_ctx* ctx, int64_t* out);
 /* execution-shape knob: 0 = auto (thread-per-parcel kernel when the (n_modes, P) shape has an instance, else 8 lanes),
  * 1 = thread per parcel, 4/8/16/32 = that many lanes cooperating on one parcel's quadrature nodes */
 int cloudy_set_lanes(cloudy_ctx* ctx, int lanes);
-/* regime sort (off by default): before the thread-per-parcel kernel, order the parcels by series length and
- * series / continued-fraction regime so that warps are homogeneous.  Results are bit-identical either way; it pays when
- * thresholds sit far in the tail for part of the ensemble (continued-fraction regime mixed into every warp). */
+/* regime sort: before the thread-per-parcel kernel, order the parcels by series length and series / continued-fraction
+ * regime so that warps are homogeneous (three small kernels; the order is reused by the stages of a fused step).
+ * Results are bit-identical either way.  on = 0 off, 1 always, 2 auto (default: from 262144 parcels, where it pays). */
 int cloudy_set_regime_sort(cloudy_ctx* ctx, int on);
 
 /* ---- device state ---------------------------------------------------------------------------- */

@@ -21,7 +21,7 @@ print("fp64 peak TFLOP/s:", ctx.measure_fp64_peak())
 u = model.ensemble(n).upload(state)
 du = model.ensemble(n)
 sort = len(sys.argv) > 4 and sys.argv[4] == "sort"
-ctx.set_regime_sort(sort)
+ctx.set_regime_sort(1 if sort else 0)
 for lanes in lanes_list:
     ctx.set_lanes(lanes)
     def run():
