@@ -123,7 +123,8 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
     const int nb_w = Grid::kPadded ? grid.count() : __reduce_max_sync(0xffffffffu, grid.count());  // loop bound
     const double e0 = fma(-2.0 * k, log_th, -X);   // exponent offset of g*E
     const double Xc = fmin(X, ser_lim - 0.5);       // Taylor centre (inside the series regime)
-    const double inv_Xc = 1.0 / Xc;
+    const double rq = inv_th / Xc;                  // r = z/X_c - 1 = (x_th - x_j) rq - 1
+    const bool warp_cf = __any_sync(0xffffffffu, !(X < ser_lim));  // any parcel of the warp with continued-fraction nodes
 
     // near nodes come first in the padded tables; they are processed AFTER the far nodes (which need the c_n table)
     int n_near_b = 0, jf = 0;
@@ -160,7 +161,7 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
             const double t_top = myCt[K * TPP_THREADS];
 #pragma unroll
             for (int i = 0; i < NPL; ++i) {
-                r[i] = (z[i] - Xc) * inv_Xc;
+                r[i] = fma(grid.tmx(j0 + i), rq, -1.0);
                 h[i] = t_top;
             }
 #pragma unroll 4
@@ -198,7 +199,8 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
         for (int i = 0; i < NPL; ++i) {
             const int j = j0 + i;
             const double gE = fast_exp(fma(k, grid.log_sum(j), e0), exp_tab);  // g_j * E_j
-            const double hs = (z[i] < ser_lim) ? h[i] : 0.0;                   // continued-fraction nodes: added below
+            double hs = h[i];
+            if (warp_cf) hs = (z[i] < ser_lim) ? hs : 0.0;  // continued-fraction nodes: added by the loop below
             double zp[MP];
             zp[0] = 1.0;
 #pragma unroll
@@ -226,7 +228,7 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
     }
 
     // ---- rare path: nodes in the continued-fraction regime (only when x_th/θ reaches the series limit) ----
-    if (__any_sync(0xffffffffu, !(X < ser_lim))) {
+    if (warp_cf) {
         double B[MP];
         B[MP - 1] = 1.0;
 #pragma unroll
@@ -371,11 +373,43 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
     double* myCt = sCt + tid;
 
     const long long n = args.n;
-    for (long long base = blockIdx.x * (long long)TPP_THREADS + (tid & ~31); base < n; base += (long long)gridDim.x * TPP_THREADS) {
+    const long long stride_all = (long long)gridDim.x * TPP_THREADS;
+    // software prefetch: the next parcel's moments are requested while the current one is being evaluated
+    auto parcel_of = [&](long long b) -> long long {
+        const long long ix = b + (tid & 31);
+        const long long q = (ix < n) ? ix : n - 1;
+        return (args.perm != nullptr) ? (long long)args.perm[q] : q;
+    };
+    double nxt[N][3];
+    long long p_next = 0;
+    {
+        const long long b0 = blockIdx.x * (long long)TPP_THREADS + (tid & ~31);
+        if (b0 < n) {
+            p_next = parcel_of(b0);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    nxt[i][q] = (q < cfg.nprog[i]) ? args.u_in[(cfg.slot0[i] + q) * args.s_in + p_next * args.ps_in] : 0.0;
+        }
+    }
+    for (long long base = blockIdx.x * (long long)TPP_THREADS + (tid & ~31); base < n; base += stride_all) {
         const long long idx = base + (tid & 31);
         const bool live = idx < n;
-        const long long qi = live ? idx : n - 1;
-        const long long p = (args.perm != nullptr) ? (long long)args.perm[qi] : qi;
+        const long long p = p_next;
+        double cur[N][3];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) cur[i][q] = nxt[i][q];
+        if (base + stride_all < n) {
+            p_next = parcel_of(base + stride_all);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    nxt[i][q] = (q < cfg.nprog[i]) ? args.u_in[(cfg.slot0[i] + q) * args.s_in + p_next * args.ps_in] : 0.0;
+        }
 
         // ---- load, (clip), normalise, parameters, moment matrix --------------------------------------
         double raw[N][3];
@@ -390,7 +424,7 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
             for (int q = 0; q < 3; ++q) {
                 raw[i][q] = 0.0;
                 if (q < np) {
-                    double v = args.u_in[(s0 + q) * args.s_in + p * args.ps_in];
+                    double v = cur[i][q];
                     if (RAIN) {
                         v = (v < 0.0) ? 0.0 : v;  // rainshaft_helpers.jl:52
                         if (args.clip_back != nullptr && live) args.clip_back[(s0 + q) * args.s_clip + p] = v;
@@ -499,13 +533,26 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
                         const int cfd = sh.cfd[ai];
                         const int cfd_w = __reduce_max_sync(0xffffffffu, cfd);
                         {   // c_n = 1/(a)_{n+1}: one division, then c_{n-1} = c_n (a+n)
-                            double prod = 1.0;
-                            for (int nn = 0; nn <= deg; ++nn) prod *= (a_top + (double)nn);
-                            double cc = 1.0 / prod;
-                            for (int nn = deg; nn >= 0; --nn) {
-                                myCt[nn * TPP_THREADS] = cc;
-                                cc *= (a_top + (double)nn);
+                            double pe = 1.0, po = 1.0;  // two independent product chains (even / odd factors)
+                            for (int nn = 0; nn + 1 <= deg; nn += 2) {
+                                pe *= (a_top + (double)nn);
+                                po *= (a_top + (double)(nn + 1));
                             }
+                            if ((deg & 1) == 0) pe *= (a_top + (double)deg);
+                            double cc = 1.0 / (pe * po);  // c_deg
+                            // c_{n-1} = c_n (a+n): two interleaved chains stepping by two
+                            double c1 = cc * (a_top + (double)deg);  // c_{deg-1}
+                            int nn = deg;
+                            for (; nn >= 2; nn -= 2) {
+                                myCt[nn * TPP_THREADS] = cc;
+                                myCt[(nn - 1) * TPP_THREADS] = c1;
+                                const double f = (a_top + (double)nn) * (a_top + (double)(nn - 1));
+                                const double f1 = (a_top + (double)(nn - 1)) * (a_top + (double)(nn - 2));
+                                cc *= f;   // c_{nn-2}
+                                c1 *= f1;  // c_{nn-3}
+                            }
+                            if (nn == 1) { myCt[TPP_THREADS] = cc; myCt[0] = c1; }
+                            else myCt[0] = cc;
                             for (int nn = deg + 1; nn <= deg_w; ++nn) myCt[nn * TPP_THREADS] = 0.0;
                         }
                         const double pre0 = nmd * nmd / (gk * gk);
