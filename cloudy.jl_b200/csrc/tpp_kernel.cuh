@@ -125,6 +125,7 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
     const double Xc = fmin(X, ser_lim - 0.5);       // Taylor centre (inside the series regime)
     const double rq = inv_th / Xc;                  // r = z/X_c - 1 = (x_th - x_j) rq - 1
     const bool warp_cf = __any_sync(0xffffffffu, !(X < ser_lim));  // any parcel of the warp with continued-fraction nodes
+    const double cf_lim = warp_cf ? ser_lim : INFINITY;
 
     // near nodes come first in the padded tables; they are processed AFTER the far nodes (which need the c_n table)
     int n_near_b = 0, jf = 0;
@@ -199,8 +200,7 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
         for (int i = 0; i < NPL; ++i) {
             const int j = j0 + i;
             const double gE = fast_exp(fma(k, grid.log_sum(j), e0), exp_tab);  // g_j * E_j
-            double hs = h[i];
-            if (warp_cf) hs = (z[i] < ser_lim) ? hs : 0.0;  // continued-fraction nodes: added by the loop below
+            const double hs = (z[i] < cf_lim) ? h[i] : 0.0;  // continued-fraction nodes: added by the loop below
             double zp[MP];
             zp[0] = 1.0;
 #pragma unroll
