@@ -201,18 +201,15 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
             const int j = j0 + i;
             const double gE = fast_exp(fma(k, grid.log_sum(j), e0), exp_tab);  // g_j * E_j
             const double hs = (z[i] < cf_lim) ? h[i] : 0.0;  // continued-fraction nodes: added by the loop below
-            double zp[MP];
-            zp[0] = 1.0;
+            // v_p = g E h_p with h_top = z^{MP-1} S, h_p = (h_{p+1} + z^p)/(k+p): carry g E z^p instead of z^p
+            double y[MP];
+            y[0] = gE;
 #pragma unroll
-            for (int p = 1; p < MP; ++p) zp[p] = zp[p - 1] * z[i];
+            for (int p = 1; p < MP; ++p) y[p] = y[p - 1] * z[i];
             double v[MP];
-            double hp = zp[MP - 1] * hs;
-            v[MP - 1] = gE * hp;
+            v[MP - 1] = y[MP - 1] * hs;
 #pragma unroll
-            for (int p = MP - 2; p >= 0; --p) {
-                hp = (hp + zp[p]) * ia[p];  // downward recurrence
-                v[p] = gE * hp;
-            }
+            for (int p = MP - 2; p >= 0; --p) v[p] = (v[p + 1] + y[p]) * ia[p];  // downward recurrence
             double w[MP];
             grid.template weights<MP>(j, w);
             int t = 0;
