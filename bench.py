@@ -306,7 +306,10 @@ def run_b200(args):
                 "hbm": {"achieved": BYTES_PER_EVAL * n / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": BYTES_PER_EVAL * n / (k_ms * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one tpp_kernel launch over 1 Mi parcels, ncu --set full
+                # (profiles/r01_tpp_kernel_c2_ncu_full_summary.txt): 84.8 + 39.3 MB vs 84 MB algorithmic (the regime-sorted gather
+                # touches 32-byte sectors for 8-byte loads); irrelevant to the FP64-bound duration
+                "traffic": 124.1e6 if n == (1 << 20) else None,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(state0.nbytes), "d2h_bytes_per_step": int(state0.nbytes),
                     "steps": e2e_steps, "api": "cloudy_coal_tendency_host (pinned host buffers)", "checksum": checksum},

@@ -20,6 +20,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -793,7 +794,11 @@ __global__ void __launch_bounds__(256) nq_kernel(const __grid_constant__ DevConf
 __global__ void __launch_bounds__(256) regime_key_kernel(const __grid_constant__ DevConfig cfg, const KArgs args, unsigned char* __restrict__ keys,
                                                          unsigned int* __restrict__ hist) {
     __shared__ unsigned int sh[256];
+    __shared__ unsigned char sdeg[kSerZ][kSerA];  // per-thread (divergent) lookups: shared memory, not the constant bank
+    __shared__ double slim[kSerA];
     sh[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < kSerZ * kSerA; i += blockDim.x) sdeg[i / kSerA][i % kSerA] = kSeriesDeg2[i / kSerA][i % kSerA];
+    if (threadIdx.x < kSerA) slim[threadIdx.x] = kSeriesLimit[threadIdx.x];
     __syncthreads();
     const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (p < args.n) {
@@ -810,10 +815,10 @@ __global__ void __launch_bounds__(256) regime_key_kernel(const __grid_constant__
             if (mp.n != 0.0) {
                 const double a_top = mp.b + (double)(cfg.Mp[i] - 1);
                 const int ai = series_a_bin(a_top);
-                const double ser_lim = kSeriesLimit[ai];
+                const double ser_lim = slim[ai];
                 const double X = cfg.thr[i] / mp.a;
                 const int zi = series_z_bin(fmin(X, ser_lim - 0.5));
-                const unsigned int deg = kSeriesDeg2[zi][ai];
+                const unsigned int deg = sdeg[zi][ai];
                 sub = (X >= ser_lim ? 1u : 0u) | (((deg >> 3) & 7u) << 1);
                 sub = sub == 0 ? 2u : sub;  // keep 0 for "empty mode"
             }
@@ -1624,6 +1629,7 @@ int cloudy_coal_tendency_host(cloudy_ctx* ctx, const double* host_m, double* hos
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int ns = ctx->dev.nslots;
     long long chunk = 131072;
+    if (const char* e = getenv("CLOUDY_PIPE_CHUNK")) chunk = std::max<long long>(1024, atoll(e));
     if (n_parcels < chunk) chunk = n_parcels;
     int rc = ensure_pipe(ctx, std::max<long long>(chunk, 1024));
     if (rc) return rc;
