@@ -327,8 +327,22 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def ensure_built():
+    """the native libraries are build products: compile them if this checkout has none (nvcc / gcc are in the image)"""
+    if not (os.path.exists(os.path.join(ROOT, "cloudy.jl_b200", "libcloudy_b200.so")) and
+            os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so"))):
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            import __graft_entry__
+            __graft_entry__.build()
+        else:
+            while not os.path.exists(os.path.join(ROOT, "cloudy.jl_b200", "libcloudy_b200.so")):
+                time.sleep(1.0)
+            time.sleep(2.0)
+
+
 def main():
     args = parse()
+    ensure_built()
     if args.impl == "reference":
         run_reference(args)
     else:
