@@ -10,7 +10,8 @@ from .helpers import (get_dist_moment_ind, get_dist_moments_ind_range, get_momen
 from .distributions import (PrimitiveParticleDistribution, ExponentialPrimitiveParticleDistribution,
                             GammaPrimitiveParticleDistribution, LognormalPrimitiveParticleDistribution,
                             MonodispersePrimitiveParticleDistribution, moment, get_moments, density, nparams,
-                            update_dist_from_moments, moment_source_helper, integrate_SimpsonEvenFast)
+                            update_dist_from_moments, moment_source_helper, integrate_SimpsonEvenFast,
+                            compute_threshold, compute_thresholds, normed_density)
 from .kernel_tensors import (CoalescenceTensor, get_normalized_kernel_tensor, check_symmetry, polyfit,
                              ConstantKernelFunction, LinearKernelFunction, HydrodynamicKernelFunction,
                              LongKernelFunction, get_normalized_kernel_func)

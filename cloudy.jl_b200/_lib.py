@@ -68,6 +68,7 @@ SIGNATURES = {
     "cloudy_moment": (_P, C.c_int32, _D, C.c_double, _D),
     "cloudy_update_dist_from_moments": (_P, C.c_int32, _D, _D, _D, _I32),
     "cloudy_moment_source_helper": (_P, C.c_int32, _D, C.c_double, C.c_double, C.c_double, C.c_int32, _D),
+    "cloudy_compute_threshold": (_P, C.c_int32, _D, C.c_double, C.c_double, _D),
     "cloudy_get_coal_ints_1": (_P, _D, _D),
     "cloudy_get_sedimentation_flux_1": (_P, C.c_int32, _I32, _D, C.c_int32, _D, _D),
     "cloudy_get_cond_evap_1": (_P, C.c_int32, _I32, _D, C.c_double, C.c_double, C.c_double, _D),

@@ -77,7 +77,7 @@ class CoalescenceData:
 
 
 def build_config(kinds: Sequence[int], coal_data: CoalescenceData, norms=None, vel=(), dz: float = 1.0, nz: int = 1,
-                 k_range=None) -> L.cloudy_config:
+                 k_range=None, moving=None) -> L.cloudy_config:
     """Marshal CoalescenceData + the drivers' ODE_parameters into the C-ABI struct."""
     cd = coal_data
     N, P = cd.N, cd.P
@@ -92,7 +92,9 @@ def build_config(kinds: Sequence[int], coal_data: CoalescenceData, norms=None, v
         cfg.nprog[i] = int(cd.NProgMoms[i])
         cfg.n_2d_ints[i] = int(cd.N_2d_ints[i])
         cfg.thresholds[i] = cd.dist_thresholds[i]
-    cfg.threshold_style = L.MOVING_THRESHOLD if isinstance(cd.threshold_style, MovingThreshold) else L.FIXED_THRESHOLD
+    if moving is None:
+        moving = isinstance(cd.threshold_style, MovingThreshold)
+    cfg.threshold_style = L.MOVING_THRESHOLD if moving else L.FIXED_THRESHOLD
     cfg.n_mom_max = cd.N_mom_max
     cfg.bins_per_log_unit = 15
     for j in range(N):
@@ -141,8 +143,10 @@ def get_coal_ints(cs, pdists, coal_data: CoalescenceData, ts: ThresholdStyle = N
             raise ValueError("NProgMoms does not match the distributions")
     ctx = ctx or default_context()
     kinds = tuple(d.kind for d in pdists)
-    cfg = build_config(kinds, coal_data, norms=(1.0, 1.0))
-    apply_config(ctx, cfg, key=("coal_ints", coal_data.uid, kinds))
+    # the 4-argument method (Coalescence.jl:152-157) reads coal_data.dist_thresholds as percentiles
+    moving = isinstance(ts, MovingThreshold) if ts is not None else isinstance(coal_data.threshold_style, MovingThreshold)
+    cfg = build_config(kinds, coal_data, norms=(1.0, 1.0), moving=moving)
+    apply_config(ctx, cfg, key=("coal_ints", coal_data.uid, kinds, moving))
     params = np.zeros((coal_data.N, 3))
     for i, d in enumerate(pdists):
         p = d.params()

@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(SUM_THREADS) moment_final_kernel(const double*
 
 // single-object evaluations (arbitrary real orders): one warp
 struct ScalarArgs {
-    int op;  // 0 moment, 1 update_dist, 2 moment_source_helper, 3 sed flux, 4 simpson
+    int op;  // 0 moment, 1 update_dist, 2 moment_source_helper, 3 sed flux, 4 simpson, 5 compute_threshold
     int kind;
     double params[3];
     double q, p1, p2, x_th;
@@ -669,6 +669,13 @@ __global__ void scalar_kernel(const ScalarArgs a) {
                     a.out[o++] = s;
                 }
             }
+        }
+    } else if (a.op == 5) {
+        // compute_threshold(pdist, percentile, minx) — ParticleDistributions.jl:747-761
+        if (lane == 0) {
+            const double th = a.params[1];
+            const double x = (a.kind == CLOUDY_GAMMA) ? th * igam_inv(a.params[2], a.q) : -th * log(1.0 - a.q);
+            a.out[0] = fmax(x, a.p1);
         }
     } else if (a.op == 4) {
         double part = 0.0;
@@ -1762,6 +1769,18 @@ int cloudy_moment_source_helper(cloudy_ctx* ctx, int32_t kind, const double* par
     if (a.n_bins < 3) return fail(CLOUDY_ERR_ARG, "n_bins must be at least 3");
     a.x_min = log(x_lb);
     a.dx = (log(x_threshold) - log(x_lb)) / a.n_bins;
+    return run_scalar(ctx, a, out, 1, nullptr);
+}
+
+int cloudy_compute_threshold(cloudy_ctx* ctx, int32_t kind, const double* params, double percentile, double minx, double* out) {
+    if (!ctx || !params || !out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (kind != CLOUDY_EXPONENTIAL && kind != CLOUDY_GAMMA)
+        return fail(CLOUDY_ERR_ARG, "MethodError: compute_threshold is defined for Exponential and Gamma distributions only");
+    ScalarArgs a;
+    memset(&a, 0, sizeof(a));
+    a.op = 5; a.kind = kind; a.q = percentile; a.p1 = minx;
+    a.params[2] = 1.0;
+    for (int i = 0; i < kind_nparams(kind); ++i) a.params[i] = params[i];
     return run_scalar(ctx, a, out, 1, nullptr);
 }
 

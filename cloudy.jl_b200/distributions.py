@@ -160,6 +160,32 @@ def integrate_SimpsonEvenFast(n_bins: int, dx: float, y, ctx=None) -> float:
     return out.value
 
 
+def compute_threshold(pdist, percentile: float = 0.97, minx: float = 1e-18, ctx=None) -> float:
+    """compute_threshold(pdist, percentile, minx) — ParticleDistributions.jl:747-761 (Exponential and Gamma only)."""
+    if pdist.kind not in (L.EXPONENTIAL, L.GAMMA):
+        raise TypeError("MethodError: no method matching compute_threshold for this distribution")
+    ctx = ctx or default_context()
+    out = C.c_double()
+    L.check(L.load().cloudy_compute_threshold(ctx.handle, pdist.kind, _params3(pdist), float(percentile), float(minx), C.byref(out)))
+    return out.value
+
+
+def compute_thresholds(pdists, percentile=0.97, ctx=None):
+    """compute_thresholds(pdists, percentile | percentiles) — ParticleDistributions.jl:721-745: Inf for the last mode."""
+    N = len(pdists)
+    pcs = list(percentile) if isinstance(percentile, (tuple, list)) else [percentile] * N
+    return tuple(math.inf if i == N - 1 else compute_threshold(pdists[i], pcs[i], ctx=ctx) for i in range(N))
+
+
+def normed_density(dist, x: float) -> float:
+    """ParticleDistributions.jl:411-416 — plotting helper, host arithmetic."""
+    if x < 0:
+        raise ValueError("Density can only be evaluated at nonnegative values.")
+    if dist.kind == L.MONODISPERSE:
+        raise TypeError("MethodError: normed_density_func is not defined for Monodisperse distributions")
+    return density(type(dist)(1.0, *dist.params()[1:]), x)
+
+
 def density(dist, x: float) -> float:
     """ParticleDistributions.jl:397-402 — not on the accelerated path (plotting helper); host arithmetic."""
     if x < 0:

@@ -160,6 +160,8 @@ int cloudy_update_dist_from_moments(cloudy_ctx* ctx, int32_t kind, const double*
 /* moment_source_helper(dist, p1, p2, x_threshold, n_bins_per_log_unit) — ParticleDistributions.jl:557-625 */
 int cloudy_moment_source_helper(cloudy_ctx* ctx, int32_t kind, const double* params, double p1, double p2,
                                 double x_threshold, int32_t n_bins_per_log_unit, double* out);
+/* compute_threshold(pdist, percentile, minx) — ParticleDistributions.jl:747-761 (Exponential: -θ log(1-p); Gamma: θ gamma_inc_inv(k, p)) */
+int cloudy_compute_threshold(cloudy_ctx* ctx, int32_t kind, const double* params, double percentile, double minx, double* out);
 /* get_coal_ints(AnalyticalCoalStyle(), pdists, coal_data[, MovingThreshold()]) for ONE set of distributions;
  * params: [n_modes][3]; out: Σ nprog doubles (normalised units, exactly the reference's return value).
  * Coalescence.jl:115-185 */

@@ -202,3 +202,34 @@ def test_get_standard_N_q(cb):
     q = cb.get_standard_N_q(pd, 1.2)
     ref = O.get_standard_N_q((O.Monodisperse(1.0, 0.5), O.Lognormal(1.0, 0.5, 2.0), O.Gamma(5.0, 10.0, 2.0)), 1.2)
     assert np.allclose((q.N_liq, q.N_rai, q.M_liq, q.M_rai), ref, rtol=1e-7)  # Lognormal: the reference integrates adaptively at sqrt(eps)
+
+
+def test_compute_thresholds(cb):
+    """test_ParticleDistributions_correctness.jl:257-268"""
+    from oracle import cloudy_oracle as O
+    pd = (cb.ExponentialPrimitiveParticleDistribution(10.0, 1.0), cb.GammaPrimitiveParticleDistribution(5.0, 10.0, 2.0))
+    assert cb.compute_threshold(pd[0], 0.75) > 1.0
+    assert cb.compute_threshold(pd[1], 0.75) > 2.0 * 10.0
+    assert abs(cb.compute_threshold(pd[0], 0.0)) < 1e-6 and abs(cb.compute_threshold(pd[1], 0.0)) < 1e-6
+    assert approx(cb.compute_thresholds(pd)[0], 3.507)
+    assert cb.compute_thresholds(pd)[1] > 1e6
+    assert approx(cb.compute_thresholds(pd, (0.5, 1.0))[0], 0.6931)
+    for k, pct in ((0.3, 0.9), (2.0, 0.97), (7.5, 0.5), (10.0, 0.999), (1.0, 0.01)):
+        got = cb.compute_threshold(cb.GammaPrimitiveParticleDistribution(1.0, 3.0, k), pct)
+        assert approx(got, O.compute_threshold(O.Gamma(1.0, 3.0, k), pct), 1e-13)
+    with pytest.raises(Exception):
+        cb.compute_threshold(cb.LognormalPrimitiveParticleDistribution(1.0, 0.0, 1.0), 0.9)
+
+
+def test_get_coal_ints_moving_threshold(cb):
+    """get_coal_ints(cs, pdists, coal_data, MovingThreshold()) — Coalescence.jl:152-185"""
+    from oracle import cloudy_oracle as O
+    Gam = cb.GammaPrimitiveParticleDistribution
+    pd = (Gam(100.0, 0.1, 1.5), Gam(1.0, 8.0, 2.5), Gam(1e-3, 400.0, 1.0))
+    ker = cb.CoalescenceTensor(np.array([[0.0, 5e-3], [5e-3, 0.0]]))
+    cdm = cb.CoalescenceData(ker, (3, 3, 3), (0.99, 0.95, 1.0), (1.0, 1.0), cb.MovingThreshold())
+    got = cb.get_coal_ints(cb.AnalyticalCoalStyle(), pd, cdm, cb.MovingThreshold())
+    ocd = O.make_coalescence_data(np.array([[0.0, 5e-3], [5e-3, 0.0]]), (3, 3, 3), (0.99, 0.95, 1.0), (1.0, 1.0), moving=True)
+    ref, sc = O.get_coal_ints((O.Gamma(100.0, 0.1, 1.5), O.Gamma(1.0, 8.0, 2.5), O.Gamma(1e-3, 400.0, 1.0)), ocd, True)
+    assert np.all(np.abs(np.array(got) - ref) <= 1e-9 * np.maximum(np.abs(ref), sc))
+    assert abs(got[1] + got[4] + got[7]) <= 1e-12 * (abs(got[1]) + abs(got[4]) + abs(got[7]))
