@@ -158,4 +158,37 @@ function get_coal_ints_b200(ctx::Context, pdists::NTuple{N}) where {N}
     Tuple(out)
 end
 
+"`rhs_condensation!` for a device ensemble (test/examples/utils/box_model_helpers.jl:55-67); `s` scalar supersaturation."
+cond_evap!(dm::Ensemble, m::Ensemble, s, ξ; ρ_l = 1000.0) =
+    check(ccall((:cloudy_cond_evap, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cdouble}, Cdouble, Cdouble, Ptr{Cvoid}),
+                m.ctx.handle, m.handle, s, C_NULL, ξ, ρ_l, dm.handle))
+
+"`compute_threshold(pdist, percentile)` (ParticleDistributions.jl:747-761) on the device."
+function compute_threshold_b200(ctx::Context, d, percentile = 0.97, minx = 1e-18)
+    out = Ref{Float64}(0)
+    check(ccall((:cloudy_compute_threshold, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Cdouble, Cdouble, Ref{Float64}),
+                ctx.handle, kind_code(d), params3(d), percentile, minx, out))
+    out[]
+end
+
+"`get_standard_N_q(pdists, size_cutoff)` → (; N_liq, N_rai, M_liq, M_rai) (ParticleDistributions.jl:634-687)."
+function get_standard_N_q_b200(ctx::Context, pdists::NTuple{N}, size_cutoff = 1e-6) where {N}
+    kinds = Int32[kind_code(d) for d in pdists]
+    params = zeros(Float64, 3, N)
+    for (i, d) in enumerate(pdists)
+        params[:, i] .= params3(d)
+    end
+    out = zeros(Float64, 4)
+    check(ccall((:cloudy_get_standard_N_q_1, lib), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Float64}, Cdouble, Ptr{Float64}),
+                ctx.handle, N, kinds, params, size_cutoff, out))
+    (; N_liq = out[1], N_rai = out[2], M_liq = out[3], M_rai = out[4])
+end
+
+"Σ over parcels of every prognostic moment (conservation diagnostic, cf. moments_sum in netcdf_helpers.jl:34-42)."
+function moment_sums(e::Ensemble, n_slots::Integer)
+    out = zeros(Float64, n_slots)
+    check(ccall((:cloudy_moment_sums, lib), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}), e.ctx.handle, e.handle, out))
+    out
+end
+
 end # module
