@@ -194,3 +194,20 @@ def lognormal_mixture(n_parcels=256, seed=SEED0 + 48):
     m = np.concatenate([_moments_from_params(L.LOGNORMAL, n1, mu1, s1, 3), _moments_from_params(L.LOGNORMAL, n2, mu2, s2, 3)], axis=1)
     m[0] = np.array([1e7, 1e-3, 2e-13, 1e5, 1e-4, 2e-13]) / _norm_factors(NProgMoms, NORMS)
     return par, m * _norm_factors(NProgMoms, NORMS)
+
+
+def three_modes_order2(n_parcels=256, seed=SEED0 + 49):
+    """A shape WITHOUT a thread-per-parcel instance (N = 3, P = 3): exercises the lane-cooperative generic kernel.
+    Exponential + Gamma + Gamma modes, symmetric order-2 tensor, thresholds (1, 50, Inf) normalised."""
+    rng = np.random.default_rng(seed)
+    NProgMoms = (2, 3, 3)
+    pd = (Exp(1e8, 1e-10), Gam(0.0, 1e-8, 1.0), Gam(0.0, 1e-6, 1.0))
+    c = np.array([[1e-9, 4.0, 2e8], [4.0, 3e8, 1e16], [2e8, 1e16, 0.0]])  # un-normalised: c_ab / (1e6 * 1e-9^(a+b)) scale
+    cd = CoalescenceData(CoalescenceTensor(c), NProgMoms, (1e-9, 5e-8, math.inf), NORMS)
+    par = ModelParameters(pdists=pd, coal_data=cd, NProgMoms=NProgMoms, norms=NORMS, dt=1.0)
+    n1 = _logu(rng, 1e1, 1e3, n_parcels); th1 = _logu(rng, 0.03, 0.5, n_parcels)
+    n2 = _logu(rng, 1e-4, 1e1, n_parcels); th2 = _logu(rng, 2.0, 40.0, n_parcels); k2 = _logu(rng, 0.5, 5.0, n_parcels)
+    n3 = _logu(rng, 1e-8, 1e-3, n_parcels); th3 = _logu(rng, 100.0, 1000.0, n_parcels); k3 = _logu(rng, 0.5, 5.0, n_parcels)
+    m = np.concatenate([_moments_from_params(L.EXPONENTIAL, n1, th1, None, 2), _moments_from_params(L.GAMMA, n2, th2, k2, 3),
+                        _moments_from_params(L.GAMMA, n3, th3, k3, 3)], axis=1)
+    return par, m * _norm_factors(NProgMoms, NORMS)

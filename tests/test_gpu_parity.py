@@ -315,3 +315,16 @@ def test_regime_sort_is_bit_identical(cb):
         plain = u2.download()
         assert np.isfinite(plain).mean() > 0.99  # extreme synthetic parcels may blow up in both orders alike
         assert np.array_equal(stepped, plain, equal_nan=True)
+
+
+def test_shape_without_tpp_instance_uses_generic_kernel(cb):
+    """(N, P) = (3, 3) has no thread-per-parcel instance: auto mode falls back to the lane-cooperative kernel,
+    lanes = 1 (thread per parcel required) reports CLOUDY_ERR_UNSUPPORTED."""
+    from cloudy_b200 import workloads as W
+    par, state = W.three_modes_order2(n_parcels=200)
+    _check_box(cb, par, state, 60, lanes=(0, 4, 8, 16, 32))
+    model = cb.CoalescenceModel(par)
+    model.ctx.set_lanes(1)
+    with pytest.raises(cb.CloudyError):
+        model.coal_tendency_host(state)
+    model.ctx.set_lanes(0)
