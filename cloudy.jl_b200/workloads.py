@@ -211,3 +211,36 @@ def three_modes_order2(n_parcels=256, seed=SEED0 + 49):
     m = np.concatenate([_moments_from_params(L.EXPONENTIAL, n1, th1, None, 2), _moments_from_params(L.GAMMA, n2, th2, k2, 3),
                         _moments_from_params(L.GAMMA, n3, th3, k3, 3)], axis=1)
     return par, m * _norm_factors(NProgMoms, NORMS)
+
+
+def random_model(rng, N, P, kinds=None, n_parcels=64, finite_thresholds=True):
+    """A random but physically shaped configuration for fuzz tests: ``kinds`` per mode (default: random Exp/Gamma, last mode
+    any of the four), symmetric random tensor with the magnitude pattern of a normalised kernel, thresholds increasing by mode."""
+    if kinds is None:
+        kinds = [int(rng.choice([L.EXPONENTIAL, L.GAMMA, L.MONODISPERSE])) for _ in range(N - 1)] + \
+                [int(rng.choice([L.EXPONENTIAL, L.GAMMA, L.MONODISPERSE, L.LOGNORMAL]))]
+    ctor = {L.EXPONENTIAL: lambda: Exp(1.0, 1.0), L.GAMMA: lambda: Gam(1.0, 1.0, 1.0), L.MONODISPERSE: lambda: Mono(1.0, 1.0),
+            L.LOGNORMAL: lambda: LogN(1.0, 0.0, 1.0)}
+    pd = tuple(ctor[k]() for k in kinds)
+    NProgMoms = tuple(3 if k in (L.GAMMA, L.LOGNORMAL) else 2 for k in kinds)
+    c = np.zeros((P, P))
+    for a in range(P):
+        for b in range(a, P):
+            c[a, b] = c[b, a] = rng.uniform(0.2, 1.0) * 5e-3 * 10.0 ** (-2.5 * (a + b - 1)) if (a + b) > 0 else rng.uniform(0.0, 1e-3)
+    scales = [0.1 * 30.0 ** i for i in range(N)]  # mean mass scale of mode i (normalised units)
+    thr = tuple((5.0 * scales[i] if finite_thresholds and rng.random() < 0.85 else math.inf) if i < N - 1 else math.inf for i in range(N))
+    cd = CoalescenceData(CoalescenceTensor(c), NProgMoms, thr, (1.0, 1.0))
+    par = ModelParameters(pdists=pd, coal_data=cd, NProgMoms=NProgMoms, norms=(1.0, 1.0), dt=1.0)
+    cols = []
+    for i, k in enumerate(kinds):
+        n = _logu(rng, 1e-2, 1e2, n_parcels) * 100.0 ** (-i)
+        th = _logu(rng, 0.3, 3.0, n_parcels) * scales[i]
+        if k == L.GAMMA:
+            cols.append(_moments_from_params(k, n, th, _logu(rng, 0.4, 6.0, n_parcels), 3))
+        elif k == L.LOGNORMAL:
+            cols.append(_moments_from_params(k, n, np.log(th), rng.uniform(0.3, 0.9, n_parcels), 3))
+        else:
+            cols.append(_moments_from_params(k, n, th, None, 2))
+    m = np.concatenate(cols, axis=1)
+    m[rng.random(n_parcels) < 0.05] = 0.0
+    return par, m
