@@ -165,6 +165,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-rank runs: keep the rank's threads (and therefore its first-touch pinned host buffers) on the CPU cores
+    closest to its GPU, so that the host<->device copies of the e2e leg do not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -177,6 +193,7 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
+        bind_to_gpu_numa_node(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # a non-default torch stream is made current for the whole run and handed to the library, so that
     # torch.cuda.Event timing brackets the library's launches (stream handle 0 would mean "private stream")
