@@ -6,7 +6,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-UNITS = ["cloudy_b200.cu", "tpp_inst_A.cu", "tpp_inst_B.cu", "tpp_inst_C.cu", "tpp_inst_D.cu"]
+UNITS = ["cloudy_b200.cu"] + [f"tpp_inst_{g}.cu" for g in "ABCDEFGH"]
 HEADERS = [os.path.join(CSRC, h) for h in ("special.cuh", "common.cuh", "tpp_kernel.cuh", "tpp_instances.inc")] + \
           [os.path.join(os.path.dirname(HERE), "include", "cloudy_b200.h")]
 LIB = os.path.join(HERE, "libcloudy_b200.so")

@@ -945,11 +945,19 @@ tpp_fn tpp_lookup_A(int, int, int);
 tpp_fn tpp_lookup_B(int, int, int);
 tpp_fn tpp_lookup_C(int, int, int);
 tpp_fn tpp_lookup_D(int, int, int);
+tpp_fn tpp_lookup_E(int, int, int);
+tpp_fn tpp_lookup_F(int, int, int);
+tpp_fn tpp_lookup_G(int, int, int);
+tpp_fn tpp_lookup_H(int, int, int);
 tpp_fn tpp_lookup(int N, int P, int model) {
     tpp_fn f = tpp_lookup_A(N, P, model);
     if (!f) f = tpp_lookup_B(N, P, model);
     if (!f) f = tpp_lookup_C(N, P, model);
     if (!f) f = tpp_lookup_D(N, P, model);
+    if (!f) f = tpp_lookup_E(N, P, model);
+    if (!f) f = tpp_lookup_F(N, P, model);
+    if (!f) f = tpp_lookup_G(N, P, model);
+    if (!f) f = tpp_lookup_H(N, P, model);
     return f;
 }
 }  // namespace cloudy

@@ -197,7 +197,7 @@ def lognormal_mixture(n_parcels=256, seed=SEED0 + 48):
 
 
 def three_modes_order2(n_parcels=256, seed=SEED0 + 49):
-    """A shape WITHOUT a thread-per-parcel instance (N = 3, P = 3): exercises the lane-cooperative generic kernel.
+    """Three modes with an order-2 tensor (N = 3, P = 3), a shape none of the reference's drivers uses.
     Exponential + Gamma + Gamma modes, symmetric order-2 tensor, thresholds (1, 50, Inf) normalised."""
     rng = np.random.default_rng(seed)
     NProgMoms = (2, 3, 3)

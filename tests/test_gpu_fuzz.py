@@ -8,8 +8,9 @@ from tests.oracle_bridge import oracle_params, tendency_close
 
 pytestmark = pytest.mark.gpu
 
-TPP_SHAPES = [(1, 1), (1, 2), (1, 5), (2, 2), (2, 3), (2, 5), (3, 2), (3, 5), (4, 2)]
-OTHER_SHAPES = [(2, 1), (2, 4), (4, 3)]
+TPP_SHAPES = [(1, 1), (1, 2), (1, 3), (1, 4), (1, 5), (2, 1), (2, 2), (2, 3), (2, 4), (2, 5), (3, 1), (3, 2), (3, 3), (3, 4), (3, 5),
+              (4, 1), (4, 2), (4, 3)]
+OTHER_SHAPES = [(4, 4), (4, 5)]  # no thread-per-parcel instance: lane-cooperative kernel only
 
 
 @pytest.mark.parametrize("N,P", TPP_SHAPES + OTHER_SHAPES)

@@ -318,11 +318,13 @@ def test_regime_sort_is_bit_identical(cb):
 
 
 def test_shape_without_tpp_instance_uses_generic_kernel(cb):
-    """(N, P) = (3, 3) has no thread-per-parcel instance: auto mode falls back to the lane-cooperative kernel,
+    """(N, P) = (4, 4) has no thread-per-parcel instance: auto mode falls back to the lane-cooperative kernel,
     lanes = 1 (thread per parcel required) reports CLOUDY_ERR_UNSUPPORTED."""
     from cloudy_b200 import workloads as W
-    par, state = W.three_modes_order2(n_parcels=200)
-    _check_box(cb, par, state, 60, lanes=(0, 4, 8, 16, 32))
+    par, state = W.three_modes_order2(n_parcels=200)  # (3, 3): both implementations
+    _check_box(cb, par, state, 60, lanes=(0, 1, 4, 8, 16, 32))
+    par, state = W.random_model(np.random.default_rng(44), 4, 4, kinds=[cb.GAMMA, cb.EXPONENTIAL, cb.GAMMA, cb.GAMMA], n_parcels=120)
+    _check_box(cb, par, state, 30, lanes=(0, 4, 8, 16, 32))
     model = cb.CoalescenceModel(par)
     model.ctx.set_lanes(1)
     with pytest.raises(cb.CloudyError):
