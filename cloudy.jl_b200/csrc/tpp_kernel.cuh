@@ -124,6 +124,8 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
     const double e0 = fma(-2.0 * k, log_th, -X);   // exponent offset of g*E
     const double Xc = fmin(X, ser_lim - 0.5);       // Taylor centre (inside the series regime)
     const double rq = inv_th / Xc;                  // r = z/X_c - 1 = (x_th - x_j) rq - 1
+    const bool capped = !(X <= ser_lim - 0.5);      // centre below x_th/θ: r does not vanish at the first nodes
+    const bool warp_capped = __any_sync(0xffffffffu, capped);
     const bool warp_cf = __any_sync(0xffffffffu, !(X < ser_lim));  // any parcel of the warp with continued-fraction nodes
     const double cf_lim = warp_cf ? ser_lim : INFINITY;
 
@@ -157,19 +159,33 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
 #pragma unroll
         for (int i = 0; i < NPL; ++i) z[i] = grid.tmx(j0 + i) * inv_th;  // (x_th - x_j)/θ
         if (near) {
-            const int K = grid.taylor_degree(j0 + NPL - 1);  // node-only degree: the same for every parcel
+            const int Kj = grid.taylor_degree(j0 + NPL - 1);  // node-only degree: the same for every parcel
             double r[NPL];
-            const double t_top = myCt[K * TPP_THREADS];
 #pragma unroll
-            for (int i = 0; i < NPL; ++i) {
-                r[i] = fma(grid.tmx(j0 + i), rq, -1.0);
-                h[i] = t_top;
-            }
+            for (int i = 0; i < NPL; ++i) r[i] = fma(grid.tmx(j0 + i), rq, -1.0);
+            if (!warp_capped) {
+                const double t_top = myCt[Kj * TPP_THREADS];
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) h[i] = t_top;
 #pragma unroll 4
-            for (int m = K - 1; m >= 0; --m) {
-                const double tm = myCt[m * TPP_THREADS];
+                for (int m = Kj - 1; m >= 0; --m) {
+                    const double tm = myCt[m * TPP_THREADS];
 #pragma unroll
-                for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], r[i], tm);
+                    for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], r[i], tm);
+                }
+            } else {
+                // a parcel whose centre is capped at the series limit sees |r| up to 0.1 at EVERY near node (r no longer
+                // vanishes with x_j/x_th): it takes the full degree; its warp-mates keep their own degree by predication
+                const int Kown = capped ? (TPP_TAYLOR_MAX - 1) : Kj;
+#pragma unroll
+                for (int i = 0; i < NPL; ++i) h[i] = 0.0;
+                for (int m = TPP_TAYLOR_MAX - 1; m >= 0; --m) {
+                    const double tm = myCt[m * TPP_THREADS];
+                    if (m <= Kown) {
+#pragma unroll
+                        for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], r[i], tm);
+                    }
+                }
             }
         } else {
             // Horner from the warp's largest degree; the own table is zero above the parcel's own degree, so the

@@ -360,3 +360,32 @@ def test_c4_full_size_properties(cb):
         ref, sc = O.rhs_coal(state[i], opar, return_scale=True)
         ok, worst = tendency_close(got[i], ref, sc, RTOL)
         assert ok, (i, worst)
+
+
+def test_wide_parameter_sweep(cb):
+    """Gamma + Exponential, threshold 0.5: shape k over [1e-3, 10] (incl. both clamps), scale θ over eight decades, so that
+    x_th/θ spans 5e-5 ... 5e3: Taylor zone, series zone, continued-fraction zone and their borders."""
+    from cloudy_b200 import workloads as W
+    par, _ = W.c2_gamma_exp(n_parcels=8)
+    rng = np.random.default_rng(2718)
+    n = 600
+    k = np.exp(rng.uniform(np.log(1e-3), np.log(10.0), n))
+    k[:20] = 10.0
+    th = np.exp(rng.uniform(np.log(1e-4), np.log(1e4), n))
+    th[20:60] = 0.5 / rng.uniform(17.0, 27.0, 40)      # x_th/θ around the series limits 18..26
+    nn = np.exp(rng.uniform(np.log(1e-3), np.log(1e3), n))
+    m1 = np.stack([nn, nn * k * th, nn * k * (k + 1) * th ** 2], axis=1)
+    n2 = np.exp(rng.uniform(np.log(1e-6), 0.0, n)); th2 = np.exp(rng.uniform(0.0, np.log(30.0), n))
+    state = np.concatenate([m1, np.stack([n2, n2 * th2], axis=1)], axis=1) * np.array([1e6, 1e-3, 1e-12, 1e6, 1e-3])
+    _check_box(cb, par, state, n, lanes=(0, 1, 8))
+    # dense sampling of the regime borders: x_th/θ from just below each series limit (18..26, by shape) to where even the
+    # lowest near node leaves the series regime (limit / 0.9), for shapes across all table columns
+    kk = np.repeat(np.array([0.05, 0.7, 1.0, 2.3, 3.9, 5.5, 7.2, 8.6, 10.0]), 40)
+    lim = np.array([18, 18, 19, 19, 20, 20, 21, 21, 22, 22, 23, 23, 24, 25, 25, 26, 26, 26], dtype=float)[np.floor(kk + 3).astype(int)]
+    X = lim - 1.0 + rng.uniform(0.0, 1.0, kk.size) * (lim / 0.9 + 2.0 - lim)
+    thb = 0.5 / X
+    nb = np.exp(rng.uniform(np.log(1e-1), np.log(1e2), kk.size))
+    m1 = np.stack([nb, nb * kk * thb, nb * kk * (kk + 1) * thb ** 2], axis=1)
+    n2 = np.full(kk.size, 0.1); th2 = np.full(kk.size, 5.0)
+    state = np.concatenate([m1, np.stack([n2, n2 * th2], axis=1)], axis=1) * np.array([1e6, 1e-3, 1e-12, 1e6, 1e-3])
+    _check_box(cb, par, state, kk.size, lanes=(0, 1, 8))
