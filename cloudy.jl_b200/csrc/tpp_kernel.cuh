@@ -110,7 +110,7 @@ struct MovingGrid {  // MovingThreshold: the grid follows the parcel's own thres
 //   h_top = 0 there and a separate, compact loop adds B_p (g Γ(a) - g E z^{MP-1} Q/P), B_p = prod_{q>=p} 1/(k+q), with
 //   Q/P the Legendre continued fraction of the upper function (forward recurrence, fixed depth) and g_j on its own.
 // ------------------------------------------------------------------------------------------------
-template <int MP, bool TAYLOR, typename Grid>
+template <int MP, int P, bool TAYLOR, typename Grid>
 __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], const Grid grid, const double k,
                                           const double inv_th, const double log_th, const double X, const double gam_top,
                                           const double (&ia)[MP], double* __restrict__ myCt, const int deg_w, const int cfd_w,
@@ -233,7 +233,8 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
             for (int p1 = 0; p1 < MP; ++p1) {
 #pragma unroll
                 for (int p2 = p1; p2 < MP; ++p2) {
-                    acc[t] = fma(w[p1], v[p2], acc[t]);
+                    // the S terms read F[a+c][b+m-c] with a,b < P, m <= 2: only entries with p1 + p2 <= 2P are ever used
+                    if (p1 + p2 <= 2 * P) acc[t] = fma(w[p1], v[p2], acc[t]);
                     ++t;
                 }
             }
@@ -280,7 +281,7 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
                 const double wx = w[p1] * xi;
 #pragma unroll
                 for (int p2 = p1; p2 < MP; ++p2) {
-                    acc[t] = fma(wx, B[p2], acc[t]);
+                    if (p1 + p2 <= 2 * P) acc[t] = fma(wx, B[p2], acc[t]);
                     ++t;
                 }
             }
@@ -581,14 +582,14 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
                             ia[MP - 1] = 0.0;
                             double F[MP * (MP + 1) / 2];
                             if (cfg.thr_style == CLOUDY_MOVING_THRESHOLD) {
-                                tpp_nodes<MP, false>(F, mg, k, inv_th, log_th, X, gam_top, ia, myCt, deg_w, cfd_w, cfd, a_top, ser_lim, sh.exp32);
+                                tpp_nodes<MP, P, false>(F, mg, k, inv_th, log_th, X, gam_top, ia, myCt, deg_w, cfd_w, cfd, a_top, ser_lim, sh.exp32);
                             } else {
                                 TableGrid tg;
                                 tg.rec = sTab + cfg.rec_off[i];
                                 tg.stride = REC_W + M;
                                 tg.n_near = cfg.rec_near[i];
                                 tg.n_far = cfg.rec_far[i];
-                                tpp_nodes<MP, true>(F, tg, k, inv_th, log_th, X, gam_top, ia, myCt, deg_w, cfd_w, cfd, a_top, ser_lim, sh.exp32);
+                                tpp_nodes<MP, P, true>(F, tg, k, inv_th, log_th, X, gam_top, ia, myCt, deg_w, cfd_w, cfd, a_top, ser_lim, sh.exp32);
                             }
                             double thp[MP];  // H = n^2 θ^{p2}/Γ(k)^2 * sum
                             thp[0] = pre0;
