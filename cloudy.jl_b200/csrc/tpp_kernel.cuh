@@ -475,6 +475,15 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
 #pragma unroll
             for (int q = 0; q < 3; ++q) res[i][q] = 0.0;
 
+        // rainshaft: a warp whose cells are all empty (rainshaft_helpers.jl:67-68) has zero coalescence source: skip the
+        // whole contraction (with the regime sort empty cells share warps)
+        const bool warp_idle = RAIN && __all_sync(0xffffffffu, cell_empty || !live);
+        double sumQ[N][3], sumR[N][3];
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+#pragma unroll
+            for (int m = 0; m < 3; ++m) { sumQ[k][m] = 0.0; sumR[k][m] = 0.0; }
+        if (!warp_idle) {
         // ---- S terms (self-collisions): truncated integrals of every mode, contracted at once ----------
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -632,11 +641,6 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
         // ---- Q and R (collisions between modes) — Coalescence.jl:260-351 -----------------------------
         // U_jk[c][b] = sum_a c^{jk}_ab Mom_j[a+c];  R_jk(m) = sum_b Mom_k[b+m] U[0][b];
         // Q_jk(m) = sum_c C(m,c) sum_b Mom_k[b+m-c] U[c][b]  (j < k)
-        double sumQ[N][3], sumR[N][3];
-#pragma unroll
-        for (int k = 0; k < N; ++k)
-#pragma unroll
-            for (int m = 0; m < 3; ++m) { sumQ[k][m] = 0.0; sumR[k][m] = 0.0; }
 #pragma unroll
         for (int k = 0; k < N; ++k) {
 #pragma unroll
@@ -674,7 +678,11 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
             }
         }
 
+        }  // !warp_idle
+
         // ---- assemble, combine with the stage update, store ---------------------------------------------
+        const bool top_level = RAIN && ((p + 1) % cfg.nz == 0);  // zero flux above the column top (rainshaft_helpers.jl:80-81)
+        const double inv_dz = 1.0 / cfg.dz;
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             const int s0 = cfg.slot0[k], np = cfg.nprog[k];
@@ -688,8 +696,8 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
                     if (RAIN) {
                         if (cell_empty) f = 0.0;
                         const double fl = args.flux[s * args.s_flux + p];
-                        const double fl_up = ((p + 1) % cfg.nz == 0) ? 0.0 : args.flux[s * args.s_flux + p + 1];  // zero flux at the top
-                        f = f + (-(fl_up - fl) / cfg.dz);  // rainshaft_helpers.jl:83-87
+                        const double fl_up = top_level ? 0.0 : args.flux[s * args.s_flux + p + 1];
+                        f = f + (-(fl_up - fl) * inv_dz);  // rainshaft_helpers.jl:83-87
                     }
                     double o;
                     if (args.tend_only) {
