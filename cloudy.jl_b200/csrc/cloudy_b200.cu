@@ -700,16 +700,22 @@ __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevCo
             const ModeParams mp = params_from_moments(kind, mn[0], mn[1], mn[2], kind == CLOUDY_GAMMA ? cfg.k_lo : -INFINITY,
                                                       kind == CLOUDY_GAMMA ? cfg.k_hi : INFINITY);
             double fl[3] = {0.0, 0.0, 0.0};
-            for (int v = 0; v < cfg.n_vel; ++v) {
-                const double beta = cfg.velb[v];
-                double mq = 0.0;
-                if (mp.n != 0.0 && kind != CLOUDY_LOGNORMAL) mq = moment_real(kind, mp.n, mp.a, mp.b, beta);
-                for (int q = 0; q < np; ++q) {
-                    if (kind == CLOUDY_LOGNORMAL) mq = (mp.n != 0.0) ? moment_real(kind, mp.n, mp.a, mp.b, (double)q + beta) : 0.0;
-                    fl[q] += -cfg.velv[v] * mq;
-                    if (kind == CLOUDY_GAMMA) mq *= mp.a * (mp.b + beta + q);
-                    else if (kind == CLOUDY_EXPONENTIAL) mq *= mp.a * (beta + q + 1.0);
-                    else mq *= mp.a;
+            if (mp.n != 0.0) {  // an empty mode (n = 0, the fallback of update_dist_from_moments) carries no flux
+                const double log_a = (kind == CLOUDY_LOGNORMAL) ? 0.0 : log(mp.a);
+                for (int v = 0; v < cfg.n_vel; ++v) {
+                    const double beta = cfg.velb[v];
+                    // moment(dist, beta): n θ^β Γ(β+k)/Γ(k) | n θ^β Γ(β+1) | n θ^β  (ParticleDistributions.jl:177-199)
+                    double mq = 0.0;
+                    if (kind == CLOUDY_GAMMA) mq = mp.n * exp(beta * log_a) * gamma_ratio(mp.b, beta);
+                    else if (kind == CLOUDY_EXPONENTIAL) mq = mp.n * exp(beta * log_a) * cfg.gam_b1[v];
+                    else if (kind == CLOUDY_MONODISPERSE) mq = mp.n * exp(beta * log_a);
+                    for (int q = 0; q < np; ++q) {
+                        if (kind == CLOUDY_LOGNORMAL) mq = moment_real(kind, mp.n, mp.a, mp.b, (double)q + beta);
+                        fl[q] += -cfg.velv[v] * mq;
+                        if (kind == CLOUDY_GAMMA) mq *= mp.a * (mp.b + beta + q);
+                        else if (kind == CLOUDY_EXPONENTIAL) mq *= mp.a * (beta + q + 1.0);
+                        else mq *= mp.a;
+                    }
                 }
             }
             for (int q = 0; q < np; ++q) args.out[(s0 + q) * args.s_out + p * args.ps_out] = fl[q] * cfg.norm[s0 + q];
@@ -1365,6 +1371,8 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
     for (int v = 0; v < d.n_vel; ++v) {
         d.velv[v] = cfg->vel[v][0] * pow(cfg->norms[1], cfg->vel[v][1]);  // rainshaft_helpers.jl:75
         d.velb[v] = cfg->vel[v][1];
+        d.gam_b1[v] = tgamma(1.0 + cfg->vel[v][1]);
+        if (!(cfg->vel[v][1] >= 0.0 && cfg->vel[v][1] < 2.0)) return fail(CLOUDY_ERR_UNSUPPORTED, "terminal-velocity exponents must be in [0, 2)");
     }
     d.nz = cfg->nz > 0 ? cfg->nz : 1;
     d.dz = cfg->dz;

@@ -40,6 +40,7 @@ struct DevConfig {
     double norm[MAXSLOT];
     double k_lo, k_hi;
     double velv[CLOUDY_MAX_VEL], velb[CLOUDY_MAX_VEL];  // v*norms[2]^beta, beta
+    double gam_b1[CLOUDY_MAX_VEL];                      // Γ(1 + beta): Exponential modes' fractional moment
     double inv_dz_unused, dz;
     const double* tab;  // device: per quad mode i at tab_off[i]: XJ[n] ELL[n] TMX[n] LZ[n] W[M][n]
 };
