@@ -1289,7 +1289,7 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
             tab.insert(tab.end(), lz.begin(), lz.end());
             for (int p = 0; p < d.M; ++p)
                 for (int j = 0; j < nb; ++j) tab.push_back(w[j] * cfg->dx[i] * pow(xj[j], (double)p));
-            {   // packed node records of the thread-per-parcel kernel: [near | far], each padded to a multiple of TPP_NPL
+            {   // packed node records of the thread-per-parcel kernel: [near | far], each padded to a multiple of tpp_npl(P)
                 static const double rho_thr[] = {1e-5, 1e-4, 1e-3, 3e-3, 1e-2, 2e-2, 3e-2, 5e-2, 7e-2, 0.1};
                 static const int k_of[] = {4, 5, 7, 9, 11, 14, 16, 19, 22, 25};
                 const int R = 5 + d.M;
@@ -1314,13 +1314,13 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
                     push_node(j, (double)kk, false);
                     ++n_near;
                 }
-                while (n_near % TPP_NPL) { push_node(0, kmax, true); ++n_near; }
+                while (n_near % tpp_npl(P)) { push_node(0, kmax, true); ++n_near; }
                 for (int j = 0; j < nb; ++j) {
                     if (!(xj[j] / T > 0.1 * (1.0 + 1e-9))) continue;
                     push_node(j, 0.0, false);
                     ++n_far;
                 }
-                while (n_far % TPP_NPL) { push_node(nb - 1, 0.0, true); ++n_far; }
+                while (n_far % tpp_npl(P)) { push_node(nb - 1, 0.0, true); ++n_far; }
                 d.rec_near[i] = n_near;
                 d.rec_far[i] = n_far;
                 (void)R;

@@ -19,7 +19,9 @@
 namespace cloudy {
 
 constexpr int TPP_THREADS = 128;
-constexpr int TPP_NPL = 3;       // nodes in flight per thread (measured: 2 → 0.70 ms, 3 → 0.66, 4 → 0.74, 5 → 0.73 on C2)
+// nodes in flight per thread (measured on C2, P = 2: 2 → 0.70 ms, 3 → 0.66, 4 → 0.74, 5 → 0.73); high-order tensors carry
+// up to 28 accumulators per node set, so they keep fewer nodes in flight
+__host__ __device__ constexpr int tpp_npl(int P) { return (void)P, 3; }  // (2 for P >= 4 measured within noise: +4 % at 1 Mi, -4 % at 16 Mi parcels on C4)
 constexpr int TPP_CT_ROWS = 64;  // series coefficients c_0..c_63
 constexpr int TPP_TAYLOR_MAX = 26;  // Taylor coefficients t_0..t_26 of the near-node expansion
 
@@ -51,7 +53,7 @@ __device__ __forceinline__ double fast_exp(double x, const double* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // Node records of the FixedThreshold grid, packed per node so that one base address serves all loads:
 //   [0] x_th - x_j   [1] ln x_j + ln(x_th - x_j)   [2] ln x_j   [3] x_j   [4] Taylor degree K_j   [5+p] w_j dx x_j^p
-// The host orders them [near nodes | far nodes], each zone padded to a multiple of TPP_NPL with zero-weight dummy
+// The host orders them [near nodes | far nodes], each zone padded to a multiple of tpp_npl(P) with zero-weight dummy
 // nodes, so the hot loop needs no index clamps and no validity selects.
 constexpr int REC_TMX = 0, REC_LSUM = 1, REC_ELL = 2, REC_X = 3, REC_K = 4, REC_W = 5;
 
@@ -117,7 +119,7 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
                                           const int cfd, const double a_top, const double ser_lim,
                                           const double* __restrict__ exp_tab) {
     constexpr int T = MP * (MP + 1) / 2;
-    constexpr int NPL = TPP_NPL;
+    constexpr int NPL = tpp_npl(P);
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.0;
     const int nb_w = Grid::kPadded ? grid.count() : __reduce_max_sync(0xffffffffu, grid.count());  // loop bound
