@@ -61,3 +61,17 @@ if "c5" in which:
     print(json.dumps({"config": "C5 ensemble on ONE GPU: Gamma+Exponential, 64 Mi parcels", "parcels": n, "rhs_ms": ms,
                       "parcel_rhs_per_s": n / ms * 1e3, "ssprk33_step_ms": ms_step, "parcel_steps_per_s": n / ms_step * 1e3,
                       "nominal_tflops": 1.96e4 * n / ms * 1e3 / 1e12, "fp64_peak_tflops": peak}))
+if "moving" in which:
+    n = 1 << 20
+    par, state = W.moving_gamma_exp(n)
+    model = cb.CoalescenceModel(par, ctx=ctx)
+    u = model.ensemble(n).upload(state); du = model.ensemble(n)
+    ms = timed(lambda: model.coal_tendency(u, du), 5)
+    print(json.dumps({"config": "MovingThreshold: Gamma+Exponential (C2 ensemble), percentile 0.97, 1 Mi parcels", "parcels": n, "ms": ms,
+                      "parcel_rhs_per_s": n / ms * 1e3}))
+    par, state = W.moving_four_modes(n)
+    model = cb.CoalescenceModel(par, ctx=ctx)
+    u = model.ensemble(n).upload(state); du = model.ensemble(n)
+    ms = timed(lambda: model.coal_tendency(u, du), 3)
+    print(json.dumps({"config": "MovingThreshold: 4 Gamma modes, percentiles (0.99,0.99,0.99,1) (box_gamma_mix_moving.jl), 1 Mi parcels", "parcels": n,
+                      "ms": ms, "parcel_rhs_per_s": n / ms * 1e3, "pair_evals_per_s": 16 * n / ms * 1e3}))
