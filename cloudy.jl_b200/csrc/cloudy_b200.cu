@@ -829,10 +829,19 @@ __global__ void __launch_bounds__(256) regime_key_kernel(const __grid_constant__
                 const double a_top = mp.b + (double)(cfg.Mp[i] - 1);
                 const int ai = series_a_bin(a_top);
                 const double ser_lim = slim[ai];
-                const double X = cfg.thr[i] / mp.a;
+                double X = cfg.thr[i] / mp.a;
+                bool flag = X >= ser_lim;  // FixedThreshold: series / continued-fraction regime
+                if (cfg.thr_style == CLOUDY_MOVING_THRESHOLD) {
+                    // x_th/θ = x_p(k) from the table's first guess (no polish needed for a sort key); the flag separates the
+                    // parcels that scale the unit grid (x_th <= 1) from those with a grid of their own
+                    double Xq = (kind == CLOUDY_GAMMA) ? igam_inv_guess(mp.b, cfg.tab + cfg.xp_off[i], cfg.xp_n, cfg.xp_k0, cfg.xp_inv_h)
+                                                       : -log(1.0 - cfg.thr[i]);
+                    X = (Xq > 0.0) ? Xq : 1.0;
+                    flag = mp.a * X > 1.0;
+                }
                 const int zi = series_z_bin(fmin(X, ser_lim - 0.5));
                 const unsigned int deg = sdeg[zi][ai];
-                sub = (X >= ser_lim ? 1u : 0u) | (((deg >> 3) & 7u) << 1);
+                sub = (flag ? 1u : 0u) | (((deg >> 3) & 7u) << 1);
                 sub = sub == 0 ? 2u : sub;  // keep 0 for "empty mode"
             }
             key |= sub << (4 * used);
@@ -873,6 +882,12 @@ __global__ void __launch_bounds__(256) regime_scatter_kernel(const unsigned char
     if (cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], cnt[threadIdx.x]);
     __syncthreads();
     if (p < n) perm[base[key] + rank] = (int)p;
+}
+
+// ln x_p(k) on the uniform k grid of igam_inv_tab (once per configuration)
+__global__ void xp_table_kernel(double p, double k0, double h, int n, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = log(igam_inv(k0 + (double)i * h, p));
 }
 
 // FP64 peak: independent FMA chains
@@ -1025,7 +1040,7 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
     bool any_quad = false;
     for (int i = 0; i < d.N - 1; ++i) any_quad = any_quad || d.quad[i];
     const bool want_sort = ctx->sort_mode == 1 || (ctx->sort_mode == 2 && args.n >= 262144);  // auto: pays from ~2e5 parcels (measured)
-    if (want_sort && any_quad && !args.params_in && d.thr_style == CLOUDY_FIXED_THRESHOLD && args.n >= 4096 && args.n < (1LL << 31)) {
+    if (want_sort && any_quad && !args.params_in && args.n >= 4096 && args.n < (1LL << 31)) {
         if (ctx->sort_cap < args.n) {
             cudaStreamSynchronize(ctx->stream);
             cudaFree(ctx->d_keys); cudaFree(ctx->d_perm);
@@ -1251,23 +1266,24 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
         d.ln_thr[i] = finite_thr && cfg->kind[i] == CLOUDY_LOGNORMAL;
         d.mono_thr[i] = finite_thr && cfg->kind[i] == CLOUDY_MONODISPERSE;
         d.quad[i] = finite_thr && (cfg->kind[i] == CLOUDY_GAMMA || cfg->kind[i] == CLOUDY_EXPONENTIAL);
-        if (d.quad[i] && moving) {
-            if (d.Mp[i] < 2) return fail(CLOUDY_ERR_ARG, "N_2d_ints too small");
-            mpmax = std::max(mpmax, d.Mp[i]);
-        }
         if (d.ln_thr[i]) {
             if (!(cfg->thresholds[i] > 0)) return fail(CLOUDY_ERR_ARG, "thresholds must be positive");
             any_ln = true;
         }
-        if (d.quad[i] && !moving) {
-            const int nb = cfg->n_bins[i];
-            if (!(cfg->thresholds[i] > 0)) return fail(CLOUDY_ERR_ARG, "thresholds must be positive");
+        if (d.quad[i]) {
+            // FixedThreshold: the host's grid for the run-constant threshold.  MovingThreshold: the unit grid (threshold 1,
+            // x_lb = 1e-5, 5*bins_per_log_unit nodes) that every parcel with x_th <= 1 scales by its own threshold.
+            const int bpl = cfg->bins_per_log_unit > 0 ? cfg->bins_per_log_unit : 15;
+            const int nb = moving ? 5 * bpl : cfg->n_bins[i];
+            const double T = moving ? 1.0 : cfg->thresholds[i];
+            const double g_xmin = moving ? log(1e-5) : cfg->x_min[i];
+            const double g_dx = moving ? (0.0 - log(1e-5)) / nb : cfg->dx[i];
+            if (!(T > 0)) return fail(CLOUDY_ERR_ARG, "thresholds must be positive");
             if (nb < 3) return fail(CLOUDY_ERR_ARG, "n_bins must be at least 3");
             if (nb > CLOUDY_MAX_NODES) return fail(CLOUDY_ERR_UNSUPPORTED, "n_bins exceeds CLOUDY_MAX_NODES");
             if (d.Mp[i] < 2) return fail(CLOUDY_ERR_ARG, "N_2d_ints too small");
             d.n_bins[i] = nb;
             d.tab_off[i] = (int)tab.size();
-            const double T = cfg->thresholds[i];
             std::vector<double> xj(nb), ell(nb), tmx(nb), lz(nb), w(nb, 0.0);
             const int e = nb + 1;
             auto addw = [&](int j, double v) { if (j >= 1 && j <= nb) w[j - 1] += v; };
@@ -1277,7 +1293,7 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
             addw(3, 43.0 / 48); addw(e - 2, 43.0 / 48);
             addw(4, 49.0 / 48); addw(e - 3, 49.0 / 48);
             for (int j = 1; j <= nb; ++j) {
-                ell[j - 1] = cfg->x_min[i] + (j - 1) * cfg->dx[i];  // logx, ParticleDistributions.jl:566
+                ell[j - 1] = g_xmin + (j - 1) * g_dx;  // logx, ParticleDistributions.jl:566
                 xj[j - 1] = exp(ell[j - 1]);
                 tmx[j - 1] = T - xj[j - 1];
                 if (!(tmx[j - 1] > 0)) return fail(CLOUDY_ERR_ARG, "grid node at or beyond the threshold");
@@ -1288,7 +1304,7 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
             tab.insert(tab.end(), tmx.begin(), tmx.end());
             tab.insert(tab.end(), lz.begin(), lz.end());
             for (int p = 0; p < d.M; ++p)
-                for (int j = 0; j < nb; ++j) tab.push_back(w[j] * cfg->dx[i] * pow(xj[j], (double)p));
+                for (int j = 0; j < nb; ++j) tab.push_back(w[j] * g_dx * pow(xj[j], (double)p));
             {   // packed node records of the thread-per-parcel kernel: [near | far], each padded to a multiple of tpp_npl(P)
                 static const double rho_thr[] = {1e-5, 1e-4, 1e-3, 3e-3, 1e-2, 2e-2, 3e-2, 5e-2, 7e-2, 0.1};
                 static const int k_of[] = {4, 5, 7, 9, 11, 14, 16, 19, 22, 25};
@@ -1299,7 +1315,7 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
                     tab2.push_back(ell[j]);
                     tab2.push_back(xj[j]);
                     tab2.push_back(kdeg);
-                    for (int p = 0; p < d.M; ++p) tab2.push_back(dummy ? 0.0 : w[j] * cfg->dx[i] * pow(xj[j], (double)p));
+                    for (int p = 0; p < d.M; ++p) tab2.push_back(dummy ? 0.0 : w[j] * g_dx * pow(xj[j], (double)p));
                 };
                 d.rec_off[i] = (int)tab2.size();
                 int n_near = 0, n_far = 0;
@@ -1359,6 +1375,17 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
     d.tpp_off = (int)tab.size();
     d.tpp_total = (int)tab2.size();
     tab.insert(tab.end(), tab2.begin(), tab2.end());
+    // MovingThreshold: ln x_p(k) tables of the Gamma modes (not staged in shared memory; filled on the device below)
+    d.xp_n = kXpN;
+    d.xp_k0 = kXpK0;
+    d.xp_inv_h = (double)(kXpN - 1) / (std::max(d.k_hi, 1.0) + 0.05 - kXpK0);
+    for (int i = 0; i < N; ++i) {
+        d.xp_off[i] = 0;
+        if (moving && d.quad[i] && cfg->kind[i] == CLOUDY_GAMMA) {
+            d.xp_off[i] = (int)tab.size();
+            tab.resize(tab.size() + kXpN, 0.0);
+        }
+    }
     cudaFree(ctx->d_tab);
     ctx->d_tab = nullptr;
     if (!tab.empty()) {
@@ -1366,6 +1393,12 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
         CUDA_TRY(cudaMemcpy(ctx->d_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     }
     d.tab = ctx->d_tab;
+    for (int i = 0; i < N; ++i)
+        if (d.xp_off[i]) {
+            xp_table_kernel<<<(kXpN + 63) / 64, 64>>>(d.thr[i], d.xp_k0, 1.0 / d.xp_inv_h, kXpN, ctx->d_tab + d.xp_off[i]);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaDeviceSynchronize());
+        }
     d.n_vel = cfg->n_vel;
     if (d.n_vel < 0 || d.n_vel > CLOUDY_MAX_VEL) return fail(CLOUDY_ERR_ARG, "n_vel out of range");
     for (int v = 0; v < d.n_vel; ++v) {

@@ -32,6 +32,7 @@ struct DevConfig {
     int bins_per_log_unit;         // MovingThreshold: per-parcel grid density (15 in the reference)
     int n_bins[MAXN], tab_off[MAXN];
     int rec_off[MAXN], rec_near[MAXN], rec_far[MAXN];  // packed node records of the thread-per-parcel kernel (tpp_kernel.cuh)
+    int xp_off[MAXN], xp_n;        // MovingThreshold: per Gamma mode, ln x_p(k) on a uniform k grid inside `tab` (special.cuh igam_inv_tab)
     int tab_total;                 // doubles of SoA grid tables the lane-cooperative kernel stages in shared memory
     int tpp_off, tpp_total;        // region of `tab` the thread-per-parcel kernel stages (node records, Gauss-Legendre rule)
     int n_vel, nz;
@@ -39,6 +40,7 @@ struct DevConfig {
     double thr[MAXN];
     double norm[MAXSLOT];
     double k_lo, k_hi;
+    double xp_k0, xp_inv_h;
     double velv[CLOUDY_MAX_VEL], velb[CLOUDY_MAX_VEL];  // v*norms[2]^beta, beta
     double gam_b1[CLOUDY_MAX_VEL];                      // Γ(1 + beta): Exponential modes' fractional moment
     double inv_dz_unused, dz;

@@ -125,6 +125,54 @@ __device__ inline double gamma_ratio(double k, double beta) {
     return exp(dl) * (num / den);
 }
 
+// Table-started inverse for a run-constant probability p (MovingThreshold percentiles, Coalescence.jl:152-185): ln x_p(a) is
+// tabulated on a uniform grid of a (filled once per configuration by igam_inv itself), interpolated with a 4-point
+// Lagrange formula, and polished with Halley steps on P(a,x) - p whose P comes from the division-free series
+//   S(x) = sum_n x^n/(a)_{n+1} = R_0 / ((a)_{N+1}),  R_n = x R_{n+1} + prod_{i=n+1..N}(a+i)   (all terms positive).
+// Each step cubes the error, so two or three steps reach the rounding level from an interpolation error of 1e-3.
+// Outside the table (a < k0, beyond the series regime, p <= 0) the general igam_inv is used.  `ga` = Gamma(a).
+constexpr double kXpK0 = 0.25;  // below this shape parameter ln x_p(a) is too steep in a to interpolate
+constexpr int kXpN = 544;
+__device__ __forceinline__ double igam_inv_guess(double a, const double* __restrict__ tab, int nt, double k0, double inv_h) {
+    const double u = (a - k0) * inv_h;
+    if (!(u >= 0.0 && u <= (double)(nt - 1))) return nan("");
+    int i = (int)u;
+    i = max(1, min(i, nt - 3));
+    const double t = u - (double)i;
+    const double y0 = __ldg(tab + i - 1), y1 = __ldg(tab + i), y2 = __ldg(tab + i + 1), y3 = __ldg(tab + i + 2);
+    const double l0 = -t * (t - 1.0) * (t - 2.0) * (1.0 / 6.0), l1 = (t + 1.0) * (t - 1.0) * (t - 2.0) * 0.5;
+    const double l2 = -(t + 1.0) * t * (t - 2.0) * 0.5, l3 = (t + 1.0) * t * (t - 1.0) * (1.0 / 6.0);
+    return exp(l0 * y0 + l1 * y1 + l2 * y2 + l3 * y3);
+}
+__device__ inline double igam_inv_tab(double a, double p, double ga, const double* __restrict__ tab, int nt, double k0, double inv_h,
+                                      const unsigned char (*deg)[18]) {
+    double x = igam_inv_guess(a, tab, nt, k0, inv_h);
+    if (!(x > 0.0) || !(p > 0.0) || !(p < 1.0) || !(x < 17.0)) return igam_inv(a, p);
+    const int ai = (int)fmin(a, 17.0);
+    const double la = log(x);
+    double lx = la;
+    for (int it = 0; it < 6; ++it) {
+        const int zi = (int)fmin(x * 1.05 + 0.5, 25.0);
+        int N = deg[zi][ai];
+        if (N == 0) return igam_inv(a, p);
+        N = min(N + 4, 63);  // the table's truncation bound is for a >= 1; a few more terms cover a in (1/4, 1)
+        double R = 1.0, Q = 1.0;
+        for (int n = N - 1; n >= 0; --n) {
+            Q *= a + (double)(n + 1);
+            R = fma(x, R, Q);
+        }
+        const double fp = exp(fma(a - 1.0, lx, -x)) / ga;  // dP/dx = x^{a-1} e^{-x}/Gamma(a)
+        const double f = fp * x * (R / (Q * a)) - p;
+        const double u = f / fp;
+        const double dx = u / (1.0 - 0.5 * u * ((a - 1.0) / x - 1.0));  // Halley
+        if (!(fabs(dx) < 0.5 * x)) return igam_inv(a, p);
+        x -= dx;
+        if (fabs(dx) <= 1e-6 * x) break;  // the next step's correction would be below 1e-17 x (cubic convergence)
+        lx = log(x);
+    }
+    return x;
+}
+
 // standard normal CDF
 __device__ __forceinline__ double norm_cdf(double t) { return 0.5 * erfc(-t * 0.7071067811865476); }
 

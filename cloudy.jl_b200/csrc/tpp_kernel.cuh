@@ -112,16 +112,20 @@ struct MovingGrid {  // MovingThreshold: the grid follows the parcel's own thres
 //   h_top = 0 there and a separate, compact loop adds B_p (g Γ(a) - g E z^{MP-1} Q/P), B_p = prod_{q>=p} 1/(k+q), with
 //   Q/P the Legendre continued fraction of the upper function (forward recurrence, fixed depth) and g_j on its own.
 // ------------------------------------------------------------------------------------------------
-template <int MP, int P, bool TAYLOR, typename Grid>
-__device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], const Grid grid, const double k,
+// MASKED (MovingThreshold only): a warp may hold parcels of both grid kinds; each kind's pass runs over the whole warp and
+// adds exact zeros for the threads with `on == false`, so a parcel's result does not depend on its warp-mates.
+template <int MP, int P, bool TAYLOR, bool MASKED, typename Grid>
+__device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], const bool on, const Grid grid, const double k,
                                           const double inv_th, const double log_th, const double X, const double gam_top,
                                           const double (&ia)[MP], double* __restrict__ myCt, const int deg_w, const int cfd_w,
                                           const int cfd, const double a_top, const double ser_lim,
                                           const double* __restrict__ exp_tab) {
     constexpr int T = MP * (MP + 1) / 2;
     constexpr int NPL = tpp_npl(P);
+    if constexpr (!MASKED) {
 #pragma unroll
-    for (int t = 0; t < T; ++t) acc[t] = 0.0;
+        for (int t = 0; t < T; ++t) acc[t] = 0.0;
+    }
     const int nb_w = Grid::kPadded ? grid.count() : __reduce_max_sync(0xffffffffu, grid.count());  // loop bound
     const double e0 = fma(-2.0 * k, log_th, -X);   // exponent offset of g*E
     const double Xc = fmin(X, ser_lim - 0.5);       // Taylor centre (inside the series regime)
@@ -217,8 +221,12 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
             const int j = j0 + i;
-            const double gE = fast_exp(fma(k, grid.log_sum(j), e0), exp_tab);  // g_j * E_j
-            const double hs = (z[i] < cf_lim) ? h[i] : 0.0;  // continued-fraction nodes: added by the loop below
+            double gE = fast_exp(fma(k, grid.log_sum(j), e0), exp_tab);  // g_j * E_j
+            double hs = (z[i] < cf_lim) ? h[i] : 0.0;  // continued-fraction nodes: added by the loop below
+            if constexpr (MASKED) {
+                gE = on ? gE : 0.0;
+                hs = on ? hs : 0.0;
+            }
             // v_p = g E h_p with h_top = z^{MP-1} S, h_p = (h_{p+1} + z^p)/(k+p): carry g E z^p instead of z^p
             double y[MP];
             y[0] = gE;
@@ -275,6 +283,7 @@ __device__ __forceinline__ void tpp_nodes(double (&acc)[MP * (MP + 1) / 2], cons
             for (int p = 1; p < MP; ++p) zt *= z;
             double xi = fma(g, gam_top, -(gE * zt) * (Qc / Pc));
             xi = cf_j ? xi : 0.0;
+            if constexpr (MASKED) xi = on ? xi : 0.0;
             double w[MP];
             grid.template weights<MP>(j, w);
             int t = 0;
@@ -537,10 +546,16 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
                         double thr = cfg.thr[i];
                         MovingGrid mg;
                         mg.nb = 3; mg.x_min = 0.0; mg.dx = 0.0; mg.T = 1.0;
+                        bool own_grid = false;  // MovingThreshold with x_th > 1: the grid's shape depends on the parcel
                         if (cfg.thr_style == CLOUDY_MOVING_THRESHOLD) {
                             const double pct = cfg.thr[i];
-                            const double Xp = (cfg.kind[i] == CLOUDY_GAMMA) ? igam_inv(k, pct) : -log(1.0 - pct);
+                            const double Xp = (cfg.kind[i] == CLOUDY_GAMMA)
+                                                  ? igam_inv_tab(k, pct, gk, cfg.tab + cfg.xp_off[i], cfg.xp_n, cfg.xp_k0, cfg.xp_inv_h, sh.deg)
+                                                  : -log(1.0 - pct);
                             thr = fmax(th * Xp, 1e-18);
+                            // x_lb = min(1e-5, 1e-5 x_th) (ParticleDistributions.jl:579): for x_th <= 1 the grid is x_th times a
+                            // parcel-independent unit grid (5 decades below the threshold, 5*bins_per_log_unit nodes)
+                            own_grid = thr > 1.0;
                             const double x_lb = fmin(1e-5, 1e-5 * thr);
                             const double nbf = floor((double)cfg.bins_per_log_unit * log10(thr / x_lb) + 1e-10);
                             mg.nb = (nbf >= 3.0 && nbf < 65536.0) ? (int)nbf : 3;
@@ -592,15 +607,35 @@ __global__ void __launch_bounds__(TPP_THREADS) tpp_kernel(const __grid_constant_
                             }
                             ia[MP - 1] = 0.0;
                             double F[MP * (MP + 1) / 2];
+                            TableGrid tg;
+                            tg.rec = sTab + cfg.rec_off[i];
+                            tg.stride = REC_W + M;
+                            tg.n_near = cfg.rec_near[i];
+                            tg.n_far = cfg.rec_far[i];
                             if (cfg.thr_style == CLOUDY_MOVING_THRESHOLD) {
-                                tpp_nodes<MP, P, false>(F, mg, k, inv_th, log_th, X, gam_top, ia, myCt, deg_w, cfd_w, cfd, a_top, ser_lim, sh.exp32);
+#pragma unroll
+                                for (int t = 0; t < MP * (MP + 1) / 2; ++t) F[t] = 0.0;
+                                // own-grid parcels first: their pass leaves the c_n table intact, the Taylor pass overwrites it
+                                if (__any_sync(0xffffffffu, own_grid && !skip))
+                                    tpp_nodes<MP, P, false, true>(F, own_grid, mg, k, inv_th, log_th, X, gam_top, ia, myCt, deg_w, cfd_w, cfd,
+                                                                  a_top, ser_lim, sh.exp32);
+                                if (__any_sync(0xffffffffu, !own_grid && !skip)) {
+                                    // unit grid: x_j = x_th ρ_j, so z_j = (1-ρ_j) X, ln x_j + ln(x_th-x_j) - 2 ln θ = ln ρ_j + ln(1-ρ_j) + 2 ln X
+                                    // (θ → 1/X in the node formulas) and the weights w_j dx x_j^p1 carry the factor x_th^p1
+                                    tpp_nodes<MP, P, true, true>(F, !own_grid, tg, k, X, -log(X), X, gam_top, ia, myCt, deg_w, cfd_w, cfd, a_top,
+                                                                 ser_lim, sh.exp32);
+                                    double sc = 1.0;
+                                    const double s1 = own_grid ? 1.0 : thr;
+#pragma unroll
+                                    for (int p1 = 1; p1 < MP; ++p1) {
+                                        sc *= s1;
+#pragma unroll
+                                        for (int p2 = p1; p2 < MP; ++p2) F[tri_ct(p1, p2, MP)] *= sc;
+                                    }
+                                }
                             } else {
-                                TableGrid tg;
-                                tg.rec = sTab + cfg.rec_off[i];
-                                tg.stride = REC_W + M;
-                                tg.n_near = cfg.rec_near[i];
-                                tg.n_far = cfg.rec_far[i];
-                                tpp_nodes<MP, P, true>(F, tg, k, inv_th, log_th, X, gam_top, ia, myCt, deg_w, cfd_w, cfd, a_top, ser_lim, sh.exp32);
+                                tpp_nodes<MP, P, true, false>(F, true, tg, k, inv_th, log_th, X, gam_top, ia, myCt, deg_w, cfd_w, cfd, a_top, ser_lim,
+                                                              sh.exp32);
                             }
                             double thp[MP];  // H = n^2 θ^{p2}/Γ(k)^2 * sum
                             thp[0] = pre0;
