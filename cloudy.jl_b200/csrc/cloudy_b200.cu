@@ -1085,7 +1085,11 @@ static int launch_rhs(cloudy_ctx* ctx, int model, const KArgs& args) {
     // lanes == 1: thread-per-parcel required; lanes in {4, 8, 16, 32}: lane-cooperative kernel
     const bool need_tpp = ctx->dev.thr_style == CLOUDY_MOVING_THRESHOLD || ctx->dev.ln_thr[0] || ctx->dev.ln_thr[1] || ctx->dev.ln_thr[2];
     if (ctx->lanes <= 1 || need_tpp) {
-        tpp_fn fn = tpp_lookup(ctx->dev.N, ctx->dev.P, model == CLOUDY_MODEL_RAINSHAFT ? MODEL_RAINSHAFT : MODEL_BOX);
+        const bool moving = ctx->dev.thr_style == CLOUDY_MOVING_THRESHOLD;
+        // the reference's column RHS calls the FixedThreshold method only (rainshaft_helpers.jl:70)
+        if (moving && model == CLOUDY_MODEL_RAINSHAFT)
+            return fail(CLOUDY_ERR_UNSUPPORTED, "MethodError: the rainshaft right-hand side has no MovingThreshold method");
+        tpp_fn fn = tpp_lookup(ctx->dev.N, ctx->dev.P, model == CLOUDY_MODEL_RAINSHAFT ? MODEL_RAINSHAFT : (moving ? MODEL_BOX_MOVING : MODEL_BOX));
         if (fn) return launch_tpp(ctx, fn, model, args);
         if (ctx->lanes == 1 || need_tpp) return fail(CLOUDY_ERR_UNSUPPORTED, "no thread-per-parcel kernel instance for this (n_modes, P)");
     }

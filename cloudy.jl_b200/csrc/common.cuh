@@ -66,7 +66,7 @@ struct KArgs {
     long long s_flux;
 };
 
-enum { MODEL_BOX = 0, MODEL_RAINSHAFT = 1 };
+enum { MODEL_BOX = 0, MODEL_RAINSHAFT = 1, MODEL_BOX_MOVING = 2 };
 
 // ------------------------------------------------------------------------------------------------
 // distribution parameters from normalised moments — ParticleDistributions.jl:456-541 — and the

@@ -5,7 +5,9 @@
 namespace cloudy {
 tpp_fn tpp_lookup_D(int N, int P, int model) {
 #define X(NN, PP)                                                                                          \
-    if (N == NN && P == PP) return model == MODEL_RAINSHAFT ? (tpp_fn)tpp_kernel<NN, PP, MODEL_RAINSHAFT> : (tpp_fn)tpp_kernel<NN, PP, MODEL_BOX>;
+    if (N == NN && P == PP)                                                                                \
+        return model == MODEL_RAINSHAFT ? (tpp_fn)tpp_kernel<NN, PP, MODEL_RAINSHAFT>                     \
+               : model == MODEL_BOX_MOVING ? (tpp_fn)tpp_kernel<NN, PP, MODEL_BOX_MOVING> : (tpp_fn)tpp_kernel<NN, PP, MODEL_BOX>;
     TPP_SHAPES_D
 #undef X
     return nullptr;
