@@ -30,26 +30,27 @@ constexpr int TPP_TAYLOR_MAX = 26;  // Taylor coefficients t_0..t_26 of the near
 
 __host__ __device__ constexpr int tri_ct(int p1, int p2, int MP) { return p1 * MP - (p1 * (p1 - 1)) / 2 + (p2 - p1); }
 
-// exp(x) for the node weights: x = n ln2/32 + r, exp(x) = 2^(n>>5) * 2^((n&31)/32) * e^r with a 32-entry table in shared
-// memory and a degree-6 polynomial on |r| <= ln2/64 (truncation 3e-18).  Valid for x <= 700 (the node weights' exponents
-// are bounded by ~k ln k); arguments below -708 return 0.  ~11 FP64 instructions instead of ~20 for the library exp.
-__device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab32) {
-    const double xc = x;
-    const double t = fma(xc, 46.16624130844683, 6755399441055744.0);  // 32/ln2, 1.5*2^52
-    const int n = __double2loint(t);
+// exp(x) for the node weights: x = n ln2/256 + r, exp(x) = 2^(n>>8) * 2^((n&255)/256) * e^r with a 256-entry table in shared
+// memory and a degree-4 polynomial on |r| <= ln2/512 (truncation 4e-17; measured error <= 1.4 ulp).  Valid for
+// -5e6 < x <= 700 (callers bound the exponent offset); results below 2^-1022 are returned as ~2^-1022 instead of 0, which
+// is far below anything the sums can resolve.  ~10 FP64 instructions instead of ~20 for the library exp, and only four
+// constants that do not fit an immediate operand.
+constexpr int TPP_EXP_TAB = 256;
+__device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab) {
+    const double t = fma(x, 369.3299304675746, 6755399441055744.0);  // 256/ln2, 1.5*2^52
+    int n = __double2loint(t);
     const double nf = t - 6755399441055744.0;
-    double r = fma(nf, -0.021660849390173098, xc);   // ln2/32, high 33 bits (nf * hi is exact)
-    r = fma(nf, -2.325192846878874e-12, r);           // ln2/32, low part
-    double p = fma(r, 1.3888888888888889e-03, 8.3333333333333332e-03);
-    p = fma(p, r, 4.1666666666666664e-02);
-    p = fma(p, r, 1.6666666666666666e-01);
+    double r = fma(nf, -0.002707604318857193, x);   // ln2/256, high 21 bits (nf * hi is exact)
+    r = fma(nf, -1.855205093371747e-09, r);          // ln2/256, low part
+    double p = fma(r, 4.1666666666666664e-02, 1.6666666666666666e-01);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    p *= tab32[n & 31];
-    const double res = __hiloint2double(__double2hiint(p) + ((n >> 5) << 20), __double2loint(p));
-    return (x >= -708.0) ? res : 0.0;  // underflow (and NaN, which the other factors of the integrand carry anyway) -> 0
+    p *= tab[n & (TPP_EXP_TAB - 1)];
+    n = max(n, -1022 * TPP_EXP_TAB);
+    return __hiloint2double(__double2hiint(p) + ((n >> 8) << 20), __double2loint(p));
 }
+constexpr double kExpOffsetMin = -1.0e6;  // lower clamp of per-parcel exponent offsets fed to fast_exp
 
 // ------------------------------------------------------------------------------------------------
 // node grids of the reference's log-spaced Simpson rule (ParticleDistributions.jl:579-585, :698-710)
@@ -186,7 +187,7 @@ struct NodeCommon {
     double* myCt;
     const double* exp_tab;
     __device__ __forceinline__ void init() {
-        e0 = fma(-2.0 * k, log_u, -X);       // exponent offset of g*E
+        e0 = fmax(fma(-2.0 * k, log_u, -X), kExpOffsetMin);  // exponent offset of g*E
         Xc = fmin(X, ser_lim - 0.5);          // Taylor centre (inside the series regime)
         rq = zs / Xc;                         // r = z/X_c - 1 = (x_th - x_j) rq - 1
         capped = !(X <= ser_lim - 0.5);       // centre below x_th/θ: r does not vanish at the first nodes
@@ -384,13 +385,12 @@ __device__ __forceinline__ void tpp_nodes_fixed(double (&acc)[MP * (MP + 1) / 2]
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.0;
     const int nb_w = grid.n_near + grid.n_far;  // loop bound
-    const double e0 = fma(-2.0 * k, log_th, -X);   // exponent offset of g*E
+    const double e0 = fmax(fma(-2.0 * k, log_th, -X), kExpOffsetMin);  // exponent offset of g*E
     const double Xc = fmin(X, ser_lim - 0.5);       // Taylor centre (inside the series regime)
     const double rq = inv_th / Xc;                  // r = z/X_c - 1 = (x_th - x_j) rq - 1
     const bool capped = !(X <= ser_lim - 0.5);      // centre below x_th/θ: r does not vanish at the first nodes
     const bool warp_capped = __any_sync(0xffffffffu, capped);
     const bool warp_cf = __any_sync(0xffffffffu, !(X < ser_lim));  // any parcel of the warp with continued-fraction nodes
-    const double cf_lim = warp_cf ? ser_lim : INFINITY;
 
     // near nodes come first in the padded tables; they are processed AFTER the far nodes (which need the c_n table)
     int n_near_b = 0, jf = 0;
@@ -473,11 +473,15 @@ __device__ __forceinline__ void tpp_nodes_fixed(double (&acc)[MP * (MP + 1) / 2]
                 for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], z[i], c0);
             }
         }
+        if (warp_cf) {  // continued-fraction nodes: added by the loop below (warp-uniform branch, rarely taken)
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) h[i] = (z[i] < ser_lim) ? h[i] : 0.0;
+        }
 #pragma unroll
         for (int i = 0; i < NPL; ++i) {
             const int j = j0 + i;
             const double gE = fast_exp(fma(k, grid.o_log_sum(j), e0), exp_tab);  // g_j * E_j
-            const double hs = (z[i] < cf_lim) ? h[i] : 0.0;  // continued-fraction nodes: added by the loop below
+            const double hs = h[i];
             // v_p = g E h_p with h_top = z^{MP-1} S, h_p = (h_{p+1} + z^p)/(k+p): carry g E z^p instead of z^p
             double y[MP];
             y[0] = gE;
@@ -626,7 +630,7 @@ __device__ __forceinline__ void tpp_s_terms(const DevConfig& cfg, const int k, c
 struct TppShared {
     unsigned char deg[kSerZ][kSerA];
     double serlim[kSerA];
-    double exp32[32];  // 2^(i/32)
+    double exp32[TPP_EXP_TAB];  // 2^(i/256)
     int cfd[kSerA];
     unsigned char kdeg_m[128];  // MovingThreshold own grids: Taylor degree bound of node m (counted from the threshold)
 };
@@ -644,7 +648,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
     for (int i = tid; i < cfg.tpp_total; i += TPP_THREADS) sTab[i] = cfg.tab[cfg.tpp_off + i];
     for (int i = tid; i < kSerZ * kSerA; i += TPP_THREADS) sh.deg[i / kSerA][i % kSerA] = kSeriesDeg2[i / kSerA][i % kSerA];
     if (tid < kSerA) { sh.cfd[tid] = kCfDepth[tid]; sh.serlim[tid] = kSeriesLimit[tid]; }
-    if (tid < 32) sh.exp32[tid] = exp2((double)tid / 32.0);
+    for (int i = tid; i < TPP_EXP_TAB; i += TPP_THREADS) sh.exp32[i] = exp2((double)i / (double)TPP_EXP_TAB);
     if (MOVING && tid < 128) {
         // same degree rule as the host's table grid (cloudy_config_set): |r| <= 1.15 ρ, ρ_m <= 10^(-m/bins_per_log_unit)
         const double rr = 1.15 * exp10(-(double)tid / (double)cfg.bins_per_log_unit);
