@@ -173,6 +173,19 @@ __device__ inline double igam_inv_tab(double a, double p, double ga, const doubl
     return x;
 }
 
+// Gamma(k) for the Gamma modes' shape parameter, k in (0, 11]: Gamma(k+12) from the Stirling series (tail < 1e-17 at
+// x >= 12) divided by the rising factorial (k)_12.  ~3x fewer instructions than tgamma; relative error ~5e-15.
+__device__ __forceinline__ double gamma_shape(double k) {
+    const double x = k + 12.0;
+    const double lg = fma(x - 0.5, log(x), -x) + (0.9189385332046727 + stirling_tail(x));  // ln(2 pi)/2
+    double pa = k * (k + 1.0), pb = (k + 2.0) * (k + 3.0);
+    pa *= (k + 4.0) * (k + 5.0);
+    pb *= (k + 6.0) * (k + 7.0);
+    pa *= (k + 8.0) * (k + 9.0);
+    pb *= (k + 10.0) * (k + 11.0);
+    return exp(lg) / (pa * pb);
+}
+
 // standard normal CDF
 __device__ __forceinline__ double norm_cdf(double t) { return 0.5 * erfc(-t * 0.7071067811865476); }
 

@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                         else finish_ln(std::integral_constant<int, M - 1>{});
                     } else {
                         const double inv_th = 1.0 / th;
-                        const double gk = (cfg.kind[i] == CLOUDY_GAMMA) ? tgamma(k) : 1.0;
+                        const double gk = (cfg.kind[i] == CLOUDY_GAMMA) ? gamma_shape(k) : 1.0;
                         const double a_top = k + (double)(Mp - 1);
                         // threshold: run-constant, or this parcel's own percentile (compute_threshold, ParticleDistributions.jl:747-761)
                         double thr = cfg.thr[i];
