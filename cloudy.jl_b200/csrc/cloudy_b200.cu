@@ -1688,7 +1688,10 @@ int cloudy_coal_tendency_host(cloudy_ctx* ctx, const double* host_m, double* hos
     if (n_parcels == 0) return CLOUDY_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int ns = ctx->dev.nslots;
-    long long chunk = 131072;
+    // measured on B200 / PCIe Gen5 x16 (tools/e2e_chunks.py, tools/pcie_probe.py: 55 GB/s one way, 44 GB/s each way when both
+    // directions run): 128 Ki-parcel chunks for ensembles around 1 Mi parcels (short fill/drain), 512 Ki from 4 Mi parcels
+    // on (41 GB/s each way, 93 % of the link's bidirectional rate)
+    long long chunk = n_parcels >= (1LL << 22) ? 524288 : 131072;
     if (const char* e = getenv("CLOUDY_PIPE_CHUNK")) chunk = std::max<long long>(1024, atoll(e));
     if (n_parcels < chunk) chunk = n_parcels;
     int rc = ensure_pipe(ctx, std::max<long long>(chunk, 1024));
