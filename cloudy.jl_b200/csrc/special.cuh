@@ -70,31 +70,42 @@ __device__ inline double simpson_weight(int j, int n_bins) {
 }
 
 // inverse of the regularised lower incomplete gamma function: x with P(a, x) = p (gamma_inc_inv(a, p, 1-p),
-// ParticleDistributions.jl:760).  Wilson-Hilferty / small-x start, Halley iterations on P(a,x) - p.
+// ParticleDistributions.jl:760).  Start: Wilson-Hilferty for a > 1, the small-x / exponential-tail forms otherwise;
+// then Halley iterations on P(a,x) - p with the second-order factor capped at 1 (so the correction never changes
+// sign) and a halving step if the iterate would leave x > 0.
 __device__ inline double igam_inv(double a, double p) {
     if (!(p > 0.0)) return (p == 0.0) ? 0.0 : nan("");
     if (!(p < 1.0)) return (p == 1.0) ? INFINITY : nan("");
+    if (!(a > 0.0)) return nan("");
     const double ga = tgamma(a);
     double x;
-    {
+    if (a > 1.0) {
         const double t = normcdfinv(p);
         const double w = 1.0 - 1.0 / (9.0 * a) + t / (3.0 * sqrt(a));
-        x = a * w * w * w;
-        const double xs = exp((log(p) + log(ga * a)) / a);  // leading term of P ~ x^a / Gamma(a+1)
-        if (!(x > 0.0) || a < 1.0 || xs < 0.3 * a) x = (xs < x || !(x > 0.0)) ? xs : x;
-        if (!(x > 0.0)) x = 1e-300;
+        x = fmax(1e-3, a * w * w * w);
+    } else {
+        const double t = 1.0 - a * (0.253 + a * 0.12);  // P(a, 1) to ~2 digits
+        x = (p < t) ? exp(log(p / t) / a) : 1.0 - log(1.0 - (p - t) / (1.0 - t));
+        const double xs = exp((log(p) + log(ga * a)) / a);  // leading term of P ~ x^a / Gamma(a+1): exact as p -> 0
+        if (xs < 0.05) x = xs;
     }
-    for (int it = 0; it < 60; ++it) {
-        const double P = igam_lower(a, x) / ga;
-        const double f = P - p;
+    if (!(x > 0.0)) x = 1e-300;
+    for (int it = 0; it < 100; ++it) {
+        const double f = igam_lower(a, x) / ga - p;
         const double fp = exp((a - 1.0) * log(x) - x) / ga;  // dP/dx
-        if (!(fp > 0.0)) break;
+        if (!(fp > 0.0) || !isfinite(fp)) {
+            // density under/overflow (x far from the root): move by a factor of two towards it
+            x = (f < 0.0) ? 2.0 * x : 0.5 * x;
+            continue;
+        }
         const double u = f / fp;
-        double dx = u / (1.0 - 0.5 * u * ((a - 1.0) / x - 1.0));  // Halley
-        if (!(fabs(dx) < 0.9 * x) && dx > 0.0) dx = 0.5 * x;      // keep x positive
+        const double dx = u / (1.0 - 0.5 * fmin(1.0, u * ((a - 1.0) / x - 1.0)));  // Halley, capped
         if (!(dx == dx)) break;
-        x -= dx;
-        if (fabs(dx) <= 2e-16 * x) break;
+        double xn = x - dx;
+        if (!(xn > 0.0)) xn = 0.5 * x;
+        const double step = fabs(xn - x);
+        x = xn;
+        if (step <= 1e-7 * x) break;  // cubic convergence: the next correction is below 1e-20 x
     }
     return x;
 }

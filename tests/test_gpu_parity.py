@@ -245,6 +245,60 @@ def test_moving_threshold(cb):
     _check_box(cb, par, state, 40)
 
 
+def _moving_mixed(cb, n, seed, klo=0.5, khi=5.0, percentile=0.97):
+    """Gamma + Exponential ensemble whose per-parcel thresholds straddle 1 (unit-grid and own-grid parcels side by side)"""
+    from cloudy_b200 import workloads as W
+    from cloudy_b200 import _lib as L
+    par, _ = W.moving_gamma_exp(n_parcels=8, percentile=percentile)
+    rng = np.random.default_rng(seed)
+    n1 = W._logu(rng, 1e1, 1e3, n); th1 = W._logu(rng, 0.02, 2.0, n); k1 = W._logu(rng, klo, khi, n)
+    n2 = W._logu(rng, 1e-6, 1e0, n); th2 = W._logu(rng, 1.0, 30.0, n)
+    m = np.concatenate([W._moments_from_params(L.GAMMA, n1, th1, k1, 3), W._moments_from_params(L.EXPONENTIAL, n2, th2, None, 2)], axis=1)
+    return par, m * W._norm_factors(par.NProgMoms, W.NORMS)
+
+
+def test_moving_threshold_mixed_grids(cb):
+    """x_th <= 1 parcels scale the unit grid, x_th > 1 parcels build their own (ParticleDistributions.jl:579-582); both kinds share
+    warps here.  Parity with the oracle, and a parcel's result must not depend on its warp-mates or on the regime sort."""
+    par, state = _moving_mixed(cb, 6000, 101)
+    got = _check_box(cb, par, state, 150)
+    model = cb.CoalescenceModel(par)
+    perm = np.random.default_rng(5).permutation(state.shape[0])
+    got_perm = model.coal_tendency_host(state[perm])
+    assert np.array_equal(got_perm, got[perm])
+    one_by_one = np.stack([model.coal_tendency_host(state[i:i + 1])[0] for i in range(40)])
+    assert np.array_equal(one_by_one, got[:40])
+    n = state.shape[0]
+    u = model.ensemble(n).upload(state); du = model.ensemble(n)
+    model.ctx.set_regime_sort(True)
+    model.coal_tendency(u, du)
+    model.ctx.set_regime_sort(False)
+    assert np.array_equal(du.download(), got)
+
+
+def test_moving_threshold_small_shape_and_extreme_percentiles(cb):
+    """shape parameters below the inverse-incomplete-gamma table (k < 1/4: general Halley iteration) and percentiles far
+    from the default"""
+    par, state = _moving_mixed(cb, 256, 102, klo=0.03, khi=0.4)
+    _check_box(cb, par, state, 60)
+    for pct in (0.999, 0.2, 0.01):
+        par, state = _moving_mixed(cb, 256, 103, percentile=pct)
+        _check_box(cb, par, state, 40)
+
+
+def test_rainshaft_has_no_moving_threshold_method(cb):
+    """the reference's column RHS calls get_coal_ints(style, pdists, coal_data) only (rainshaft_helpers.jl:70)"""
+    from cloudy_b200 import workloads as W
+    par, cols = W.c3_rainshaft(2, 8)
+    cd = cb.CoalescenceData(W.linear_tensor(5.0), par.NProgMoms, (0.97, 1.0), W.NORMS, cb.MovingThreshold())
+    par2 = type(par)(**{**vars(par), "coal_data": cd})
+    model = cb.CoalescenceModel(par2, nz=8)
+    st = cols.reshape(-1, cols.shape[-1])
+    u = model.ensemble(st.shape[0]).upload(st); du = model.ensemble(st.shape[0])
+    with pytest.raises(Exception, match="MovingThreshold"):
+        model.rainshaft_rhs(u, du)
+
+
 def test_lognormal_mode_with_threshold(cb):
     """box_lognorm_mixture.jl: the reference nests two adaptive QuadGK calls at rtol sqrt(eps) = 1.5e-8, so parity with
     the (scipy.integrate.quad) restatement is asserted at 1e-7 of the term scale, not 1e-9."""
