@@ -804,51 +804,71 @@ __global__ void __launch_bounds__(256) nq_kernel(const __grid_constant__ DevConf
 // the same series / continued-fraction regime.  Purely a performance hint — a parcel's result does not depend on
 // its position — so the order may be reused across the stages of a time step.
 // ------------------------------------------------------------------------------------------------
+// The key is only a scheduling hint, so the distribution parameters are rebuilt in single precision (the FP32 pipe is idle
+// in this library; FP64 divisions would make this kernel cost 6 % of a C2 step) and the block histogram is warp-aggregated.
+constexpr int KEY_PER_THREAD = 4;
 __global__ void __launch_bounds__(256) regime_key_kernel(const __grid_constant__ DevConfig cfg, const KArgs args, unsigned char* __restrict__ keys,
                                                          unsigned int* __restrict__ hist) {
     __shared__ unsigned int sh[256];
     __shared__ unsigned char sdeg[kSerZ][kSerA];  // per-thread (divergent) lookups: shared memory, not the constant bank
-    __shared__ double slim[kSerA];
+    __shared__ float slim[kSerA];
     sh[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < kSerZ * kSerA; i += blockDim.x) sdeg[i / kSerA][i % kSerA] = kSeriesDeg2[i / kSerA][i % kSerA];
-    if (threadIdx.x < kSerA) slim[threadIdx.x] = kSeriesLimit[threadIdx.x];
+    if (threadIdx.x < kSerA) slim[threadIdx.x] = (float)kSeriesLimit[threadIdx.x];
     __syncthreads();
-    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (p < args.n) {
+    const float k_lo = (float)cfg.k_lo, k_hi = (float)cfg.k_hi;
+    for (int r = 0; r < KEY_PER_THREAD; ++r) {
+        const long long p = ((long long)blockIdx.x * KEY_PER_THREAD + r) * blockDim.x + threadIdx.x;
+        const bool live = p < args.n;
         unsigned int key = 0;
-        int used = 0;
-        for (int i = 0; i < cfg.N - 1 && used < 2; ++i) {
-            if (!cfg.quad[i]) continue;
-            const int s0 = cfg.slot0[i], np = cfg.nprog[i], kind = cfg.kind[i];
-            double m[3] = {0.0, 0.0, 0.0};
-            for (int q = 0; q < np; ++q) m[q] = args.u_in[(s0 + q) * args.s_in + p * args.ps_in] / cfg.norm[s0 + q];
-            const ModeParams mp = params_from_moments(kind, m[0], m[1], m[2], kind == CLOUDY_GAMMA ? cfg.k_lo : -INFINITY,
-                                                      kind == CLOUDY_GAMMA ? cfg.k_hi : INFINITY);
-            unsigned int sub = 0;
-            if (mp.n != 0.0) {
-                const double a_top = mp.b + (double)(cfg.Mp[i] - 1);
-                const int ai = series_a_bin(a_top);
-                const double ser_lim = slim[ai];
-                double X = cfg.thr[i] / mp.a;
-                bool flag = X >= ser_lim;  // FixedThreshold: series / continued-fraction regime
-                if (cfg.thr_style == CLOUDY_MOVING_THRESHOLD) {
-                    // x_th/θ = x_p(k) from the table's first guess (no polish needed for a sort key); the flag separates the
-                    // parcels that scale the unit grid (x_th <= 1) from those with a grid of their own
-                    double Xq = (kind == CLOUDY_GAMMA) ? igam_inv_guess(mp.b, cfg.tab + cfg.xp_off[i], cfg.xp_n, cfg.xp_k0, cfg.xp_inv_h)
-                                                       : -log(1.0 - cfg.thr[i]);
-                    X = (Xq > 0.0) ? Xq : 1.0;
-                    flag = mp.a * X > 1.0;
+        if (live) {
+            int used = 0;
+            for (int i = 0; i < cfg.N - 1 && used < 2; ++i) {
+                if (!cfg.quad[i]) continue;
+                const int s0 = cfg.slot0[i], np = cfg.nprog[i], kind = cfg.kind[i];
+                float m[3] = {0.f, 0.f, 0.f};
+                for (int q = 0; q < np; ++q) m[q] = (float)args.u_in[(s0 + q) * args.s_in + p * args.ps_in] / (float)cfg.norm[s0 + q];
+                unsigned int sub = 0;
+                if (m[0] > 2.220446e-16f && m[1] > 2.220446e-16f) {  // update_dist_from_moments' non-empty test
+                    const float mean = m[1] / m[0];
+                    float kk = 1.f;
+                    if (kind == CLOUDY_GAMMA) {
+                        kk = mean / (m[2] / m[1] - mean);
+                        kk = fmaxf(k_lo, fminf(k_hi, kk));
+                        if (!(kk == kk)) kk = k_hi;
+                    }
+                    const float theta = mean / kk;
+                    const float a_top = kk + (float)(cfg.Mp[i] - 1);
+                    const int ai = (int)fminf(fmaxf(a_top, 0.f), (float)(kSerA - 1));
+                    const float ser_lim = slim[ai];
+                    float X = (float)cfg.thr[i] / theta;
+                    bool flag = X >= ser_lim;  // FixedThreshold: series / continued-fraction regime
+                    if (cfg.thr_style == CLOUDY_MOVING_THRESHOLD) {
+                        // x_th/θ = x_p(k) from the table's first guess (no polish needed for a sort key); the flag separates the
+                        // parcels that scale the unit grid (x_th <= 1) from those with a grid of their own
+                        const double Xq = (kind == CLOUDY_GAMMA)
+                                              ? igam_inv_guess((double)kk, cfg.tab + cfg.xp_off[i], cfg.xp_n, cfg.xp_k0, cfg.xp_inv_h)
+                                              : -log(1.0 - cfg.thr[i]);
+                        X = (Xq > 0.0) ? (float)Xq : 1.f;
+                        flag = theta * X > 1.f;
+                    }
+                    const float zc = fminf(X, ser_lim - 0.5f);
+                    const int zi = (zc >= 0.f) ? (int)fminf(zc, (float)(kSerZ - 1)) : 0;
+                    const unsigned int deg = sdeg[zi][ai];
+                    sub = (flag ? 1u : 0u) | (((deg >> 3) & 7u) << 1);
+                    sub = sub == 0 ? 2u : sub;  // keep 0 for "empty mode"
                 }
-                const int zi = series_z_bin(fmin(X, ser_lim - 0.5));
-                const unsigned int deg = sdeg[zi][ai];
-                sub = (flag ? 1u : 0u) | (((deg >> 3) & 7u) << 1);
-                sub = sub == 0 ? 2u : sub;  // keep 0 for "empty mode"
+                key |= sub << (4 * used);
+                ++used;
             }
-            key |= sub << (4 * used);
-            ++used;
+            keys[p] = (unsigned char)key;
         }
-        keys[p] = (unsigned char)key;
-        atomicAdd(&sh[key], 1u);
+        // warp-aggregated histogram update: one shared-memory atomic per distinct key in the warp
+        const unsigned int act = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const unsigned int peers = __match_any_sync(act, key);
+            if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&sh[key], (unsigned int)__popc(peers));
+        }
     }
     __syncthreads();
     if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
@@ -874,9 +894,18 @@ __global__ void __launch_bounds__(256) regime_scatter_kernel(const unsigned char
     __syncthreads();
     const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     unsigned int key = 0, rank = 0;
-    if (p < n) {
+    const bool live = p < n;
+    const unsigned int act = __ballot_sync(0xffffffffu, live);
+    if (live) {
+        // warp-aggregated ranking: the lowest lane of each key group reserves the group's slots
         key = keys[p];
-        rank = atomicAdd(&cnt[key], 1u);
+        const unsigned int peers = __match_any_sync(act, key);
+        const int leader = __ffs(peers) - 1;
+        const unsigned int lane = threadIdx.x & 31;
+        unsigned int base_w = 0;
+        if ((int)lane == leader) base_w = atomicAdd(&cnt[key], (unsigned int)__popc(peers));
+        base_w = __shfl_sync(peers, base_w, leader);
+        rank = base_w + (unsigned int)__popc(peers & ((1u << lane) - 1u));
     }
     __syncthreads();
     if (cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], cnt[threadIdx.x]);
@@ -1054,8 +1083,9 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
         if (!ctx->perm_valid || ctx->perm_n != args.n) {
             CUDA_TRY(cudaMemsetAsync(ctx->d_hist, 0, sizeof(unsigned int) * 512, ctx->stream));
             const unsigned blocks = (unsigned)((args.n + 255) / 256);
+            const unsigned key_blocks = (unsigned)((args.n + 256 * KEY_PER_THREAD - 1) / (256 * KEY_PER_THREAD));
             void* kp[4] = {(void*)&ctx->dev, (void*)&args, (void*)&ctx->d_keys, (void*)&ctx->d_hist};
-            CUDA_TRY(cudaLaunchKernel((const void*)regime_key_kernel, dim3(blocks), dim3(256), kp, 0, ctx->stream));
+            CUDA_TRY(cudaLaunchKernel((const void*)regime_key_kernel, dim3(key_blocks), dim3(256), kp, 0, ctx->stream));
             unsigned int* cursor = ctx->d_hist + 256;
             regime_scan_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_hist, cursor);
             regime_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_keys, cursor, ctx->d_perm, args.n);
