@@ -326,6 +326,9 @@ __device__ __forceinline__ void tpp_cf_nodes(double (&acc)[MP * (MP + 1) / 2], c
 #pragma unroll
     for (int p = MP - 2; p >= 0; --p) B[p] = B[p + 1] * C.ia[p];
     const int n_all = grid.near_count() + grid.far_count();
+    double G[MP];  // G[p1] = sum_j w_j dx x_j^p1 xi_j; the p2 dependence is the node-independent factor B[p2]
+#pragma unroll
+    for (int p = 0; p < MP; ++p) G[p] = 0.0;
 #pragma unroll 1
     for (int jj = 0; jj < n_all; ++jj) {
         const int hd = (jj < grid.near_count()) ? grid.near_handle(jj) : grid.far_handle(jj - grid.near_count());
@@ -348,8 +351,8 @@ __device__ __forceinline__ void tpp_cf_nodes(double (&acc)[MP * (MP + 1) / 2], c
             const double Qn = fma(bb, Qc, an * Qm);
             Pm = Pc; Pc = Pn; Qm = Qc; Qc = Qn;
         }
-        const double gE = exp(fma(C.k, grid.log_sum(hd, aux), C.e0));
-        const double g = exp(fma(C.k, grid.ell(hd) - C.log_u, -(grid.x(hd) * C.zs)));  // (x_j/θ)^k e^{-x_j/θ}
+        const double gE = fast_exp(fma(C.k, grid.log_sum(hd, aux), C.e0), C.exp_tab);
+        const double g = fast_exp(fmax(fma(C.k, grid.ell(hd) - C.log_u, -(grid.x(hd) * C.zs)), kExpOffsetMin), C.exp_tab);  // (x_j/θ)^k e^{-x_j/θ}
         double zt = 1.0;
 #pragma unroll
         for (int p = 1; p < MP; ++p) zt *= z;
@@ -358,15 +361,16 @@ __device__ __forceinline__ void tpp_cf_nodes(double (&acc)[MP * (MP + 1) / 2], c
         if constexpr (MASKED) xi = on ? xi : 0.0;
         double w[MP];
         grid.template weights<MP>(hd, aux, false, w);
-        int t = 0;
 #pragma unroll
-        for (int p1 = 0; p1 < MP; ++p1) {
-            const double wx = w[p1] * xi;
+        for (int p1 = 0; p1 < MP; ++p1) G[p1] = fma(w[p1], xi, G[p1]);
+    }
+    int t = 0;
 #pragma unroll
-            for (int p2 = p1; p2 < MP; ++p2) {
-                if (p1 + p2 <= 2 * P) acc[t] = fma(wx, B[p2], acc[t]);
-                ++t;
-            }
+    for (int p1 = 0; p1 < MP; ++p1) {
+#pragma unroll
+        for (int p2 = p1; p2 < MP; ++p2) {
+            if (p1 + p2 <= 2 * P) acc[t] = fma(G[p1], B[p2], acc[t]);
+            ++t;
         }
     }
 }
@@ -512,6 +516,9 @@ __device__ __forceinline__ void tpp_nodes_fixed(double (&acc)[MP * (MP + 1) / 2]
         B[MP - 1] = 1.0;
 #pragma unroll
         for (int p = MP - 2; p >= 0; --p) B[p] = B[p + 1] * ia[p];
+        double G[MP];  // G[p1] = sum_j w_j dx x_j^p1 xi_j; the p2 dependence is the node-independent factor B[p2]
+#pragma unroll
+        for (int p = 0; p < MP; ++p) G[p] = 0.0;
 #pragma unroll 1
         for (int j = 0; j < nb_w; ++j) {
             const double z = grid.o_tmx(j) * inv_th;
@@ -531,8 +538,8 @@ __device__ __forceinline__ void tpp_nodes_fixed(double (&acc)[MP * (MP + 1) / 2]
                 const double Qn = fma(bb, Qc, an * Qm);
                 Pm = Pc; Pc = Pn; Qm = Qc; Qc = Qn;
             }
-            const double gE = exp(fma(k, grid.o_log_sum(j), e0));
-            const double g = exp(fma(k, grid.ell(j) - log_th, -(grid.x(j) * inv_th)));  // (x_j/θ)^k e^{-x_j/θ}
+            const double gE = fast_exp(fma(k, grid.o_log_sum(j), e0), exp_tab);
+            const double g = fast_exp(fmax(fma(k, grid.ell(j) - log_th, -(grid.x(j) * inv_th)), kExpOffsetMin), exp_tab);  // (x_j/θ)^k e^{-x_j/θ}
             double zt = 1.0;
 #pragma unroll
             for (int p = 1; p < MP; ++p) zt *= z;
@@ -540,15 +547,16 @@ __device__ __forceinline__ void tpp_nodes_fixed(double (&acc)[MP * (MP + 1) / 2]
             xi = cf_j ? xi : 0.0;
             double w[MP];
             grid.template weights<MP>(j, 0.0, true, w);
-            int t = 0;
 #pragma unroll
-            for (int p1 = 0; p1 < MP; ++p1) {
-                const double wx = w[p1] * xi;
+            for (int p1 = 0; p1 < MP; ++p1) G[p1] = fma(w[p1], xi, G[p1]);
+        }
+        int t = 0;
 #pragma unroll
-                for (int p2 = p1; p2 < MP; ++p2) {
-                    if (p1 + p2 <= 2 * P) acc[t] = fma(wx, B[p2], acc[t]);
-                    ++t;
-                }
+        for (int p1 = 0; p1 < MP; ++p1) {
+#pragma unroll
+            for (int p2 = p1; p2 < MP; ++p2) {
+                if (p1 + p2 <= 2 * P) acc[t] = fma(G[p1], B[p2], acc[t]);
+                ++t;
             }
         }
     }
