@@ -166,7 +166,7 @@ class ClockSampler:
 
 
 def bind_to_gpu_numa_node(index):
-    """Multi-rank runs: keep the rank's threads (and therefore its first-touch pinned host buffers) on the CPU cores
+    """Keep the rank's threads (and therefore its first-touch pinned host buffers) on the CPU cores
     closest to its GPU, so that the host<->device copies of the e2e leg do not cross sockets."""
     try:
         import pynvml
@@ -192,8 +192,9 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    bind_to_gpu_numa_node(local)
     if world > 1:
-        bind_to_gpu_numa_node(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # a non-default torch stream is made current for the whole run and handed to the library, so that
     # torch.cuda.Event timing brackets the library's launches (stream handle 0 would mean "private stream")
@@ -279,8 +280,8 @@ def run_b200(args):
     h_in = torch.from_numpy(state0).pin_memory()
     h_out = torch.empty_like(h_in).pin_memory()
     hin_np, hout_np = h_in.numpy(), h_out.numpy()
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
+    e2e_steps = max(3, args.steps)
+    for _ in range(3):
         model.coal_tendency_host(hin_np, hout_np)
     barrier()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -324,9 +325,9 @@ def run_b200(args):
                         "frac": BYTES_PER_EVAL * n / (k_ms * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
                 # dram__bytes_read.sum + dram__bytes_write.sum of one tpp_kernel launch over 1 Mi parcels, ncu --set full
-                # (profiles/r01_tpp_kernel_c2_ncu_full_summary.txt): 84.8 + 39.3 MB vs 84 MB algorithmic (the regime-sorted gather
+                # (profiles/r01_tpp_kernel_c2_ncu_full_summary.txt): 84.5 + 39.1 MB vs 84 MB algorithmic (the regime-sorted gather
                 # touches 32-byte sectors for 8-byte loads); irrelevant to the FP64-bound duration
-                "traffic": 124.1e6 if n == (1 << 20) else None,
+                "traffic": 123.6e6 if n == (1 << 20) else None,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(state0.nbytes), "d2h_bytes_per_step": int(state0.nbytes),
                     "steps": e2e_steps, "api": "cloudy_coal_tendency_host (pinned host buffers)", "checksum": checksum},
@@ -334,6 +335,7 @@ def run_b200(args):
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
+            os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core again
             threads = host_threads()
             rate, ns, dt = cpu_rate(par, state0, args.cpu_seconds, threads)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
