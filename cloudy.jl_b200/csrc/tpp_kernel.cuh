@@ -24,7 +24,7 @@ constexpr int TPP_THREADS = 128;
 __host__ __device__ constexpr int tpp_npl(int P) { return (void)P, 3; }  // (2 for P >= 4 measured within noise: +4 % at 1 Mi, -4 % at 16 Mi parcels on C4)
 // resident blocks per SM the register allocation must allow (168 registers for 3 blocks of 128 threads): the small shapes
 // fit, the others take up to 255 registers and run 2 blocks
-__host__ __device__ constexpr int tpp_min_blocks(int N, int P, int model) { return (N * P <= 4 && P <= 2 && model != MODEL_BOX_MOVING) ? 3 : 2; }
+__host__ __device__ constexpr int tpp_min_blocks(int N, int P, int model) { return (N * P <= 4 && N <= 3 && model != MODEL_BOX_MOVING) ? 3 : 2; }
 constexpr int TPP_CT_ROWS = 64;  // series coefficients c_0..c_63
 constexpr int TPP_TAYLOR_MAX = 26;  // Taylor coefficients t_0..t_26 of the near-node expansion
 
