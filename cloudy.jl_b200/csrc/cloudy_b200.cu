@@ -812,22 +812,43 @@ __global__ void __launch_bounds__(256) regime_key_kernel(const __grid_constant__
     __shared__ unsigned int sh[256];
     __shared__ unsigned char sdeg[kSerZ][kSerA];  // per-thread (divergent) lookups: shared memory, not the constant bank
     __shared__ float slim[kSerA];
+    // the (at most two) thresholded modes that enter the key
+    int qm[2] = {-1, -1}, n_used = 0;
+    for (int i = 0; i < cfg.N - 1 && n_used < 2; ++i)
+        if (cfg.quad[i]) qm[n_used++] = i;
+    // all loads of the thread's KEY_PER_THREAD parcels are issued before any arithmetic (the kernel is DRAM-latency bound)
+    double raw[KEY_PER_THREAD][2][3];
+#pragma unroll
+    for (int r = 0; r < KEY_PER_THREAD; ++r) {
+        const long long p = ((long long)blockIdx.x * KEY_PER_THREAD + r) * blockDim.x + threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                raw[r][u][q] = 0.0;
+                if (p < args.n && u < n_used && q < cfg.nprog[qm[u]])
+                    raw[r][u][q] = __ldg(args.u_in + (cfg.slot0[qm[u]] + q) * args.s_in + p * args.ps_in);
+            }
+    }
     sh[threadIdx.x] = 0;
     for (int i = threadIdx.x; i < kSerZ * kSerA; i += blockDim.x) sdeg[i / kSerA][i % kSerA] = kSeriesDeg2[i / kSerA][i % kSerA];
     if (threadIdx.x < kSerA) slim[threadIdx.x] = (float)kSeriesLimit[threadIdx.x];
     __syncthreads();
     const float k_lo = (float)cfg.k_lo, k_hi = (float)cfg.k_hi;
+#pragma unroll
     for (int r = 0; r < KEY_PER_THREAD; ++r) {
         const long long p = ((long long)blockIdx.x * KEY_PER_THREAD + r) * blockDim.x + threadIdx.x;
         const bool live = p < args.n;
         unsigned int key = 0;
         if (live) {
-            int used = 0;
-            for (int i = 0; i < cfg.N - 1 && used < 2; ++i) {
-                if (!cfg.quad[i]) continue;
-                const int s0 = cfg.slot0[i], np = cfg.nprog[i], kind = cfg.kind[i];
-                float m[3] = {0.f, 0.f, 0.f};
-                for (int q = 0; q < np; ++q) m[q] = (float)args.u_in[(s0 + q) * args.s_in + p * args.ps_in] / (float)cfg.norm[s0 + q];
+#pragma unroll
+            for (int used = 0; used < 2; ++used) {
+                if (used >= n_used) break;
+                const int i = qm[used];
+                const int s0 = cfg.slot0[i], kind = cfg.kind[i];
+                float m[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) m[q] = (float)raw[r][used][q] / (float)cfg.norm[s0 + q];
                 unsigned int sub = 0;
                 if (m[0] > 2.220446e-16f && m[1] > 2.220446e-16f) {  // update_dist_from_moments' non-empty test
                     const float mean = m[1] / m[0];
@@ -859,7 +880,6 @@ __global__ void __launch_bounds__(256) regime_key_kernel(const __grid_constant__
                     sub = sub == 0 ? 2u : sub;  // keep 0 for "empty mode"
                 }
                 key |= sub << (4 * used);
-                ++used;
             }
             keys[p] = (unsigned char)key;
         }
@@ -874,43 +894,58 @@ __global__ void __launch_bounds__(256) regime_key_kernel(const __grid_constant__
     if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
-__global__ void __launch_bounds__(256) regime_scan_kernel(const unsigned int* __restrict__ hist, unsigned int* __restrict__ cursor) {
-    __shared__ unsigned int sh[256];
-    sh[threadIdx.x] = hist[threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int run = 0;
-        for (int i = 0; i < 256; ++i) { const unsigned int c = sh[i]; sh[i] = run; run += c; }
-    }
-    __syncthreads();
-    cursor[threadIdx.x] = sh[threadIdx.x];
-}
-
-__global__ void __launch_bounds__(256) regime_scatter_kernel(const unsigned char* __restrict__ keys, unsigned int* __restrict__ cursor,
-                                                             int* __restrict__ perm, long long n) {
+// Stable-per-block counting-sort scatter.  Every block rebuilds the exclusive prefix of the 256-bin histogram itself (no
+// separate scan launch) and reserves its slots per bin with one global atomic; `fill` starts at zero.
+__global__ void __launch_bounds__(256) regime_scatter_kernel(const unsigned char* __restrict__ keys, const unsigned int* __restrict__ hist,
+                                                             unsigned int* __restrict__ fill, int* __restrict__ perm, long long n) {
     __shared__ unsigned int cnt[256];
     __shared__ unsigned int base[256];
-    cnt[threadIdx.x] = 0;
+    __shared__ unsigned int pre[256];
+    const unsigned int tid = threadIdx.x, lane = tid & 31;
+    cnt[tid] = 0;
+    unsigned int key[KEY_PER_THREAD], rank[KEY_PER_THREAD];
+#pragma unroll
+    for (int r = 0; r < KEY_PER_THREAD; ++r) {
+        const long long p = ((long long)blockIdx.x * KEY_PER_THREAD + r) * blockDim.x + tid;
+        key[r] = (p < n) ? keys[p] : 0u;
+    }
+    // exclusive prefix of the histogram (Hillis-Steele over the block)
+    const unsigned int own = hist[tid];
+    pre[tid] = own;
     __syncthreads();
-    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    unsigned int key = 0, rank = 0;
-    const bool live = p < n;
-    const unsigned int act = __ballot_sync(0xffffffffu, live);
-    if (live) {
-        // warp-aggregated ranking: the lowest lane of each key group reserves the group's slots
-        key = keys[p];
-        const unsigned int peers = __match_any_sync(act, key);
-        const int leader = __ffs(peers) - 1;
-        const unsigned int lane = threadIdx.x & 31;
-        unsigned int base_w = 0;
-        if ((int)lane == leader) base_w = atomicAdd(&cnt[key], (unsigned int)__popc(peers));
-        base_w = __shfl_sync(peers, base_w, leader);
-        rank = base_w + (unsigned int)__popc(peers & ((1u << lane) - 1u));
+    for (int off = 1; off < 256; off <<= 1) {
+        const unsigned int v = (tid >= (unsigned)off) ? pre[tid - off] : 0u;
+        __syncthreads();
+        pre[tid] += v;
+        __syncthreads();
+    }
+    const unsigned int excl = pre[tid] - own;
+    __syncthreads();
+    pre[tid] = excl;
+#pragma unroll
+    for (int r = 0; r < KEY_PER_THREAD; ++r) {
+        const long long p = ((long long)blockIdx.x * KEY_PER_THREAD + r) * blockDim.x + tid;
+        const bool live = p < n;
+        const unsigned int act = __ballot_sync(0xffffffffu, live);
+        rank[r] = 0;
+        if (live) {
+            // warp-aggregated ranking: the lowest lane of each key group reserves the group's slots
+            const unsigned int peers = __match_any_sync(act, key[r]);
+            const int leader = __ffs(peers) - 1;
+            unsigned int base_w = 0;
+            if ((int)lane == leader) base_w = atomicAdd(&cnt[key[r]], (unsigned int)__popc(peers));
+            base_w = __shfl_sync(peers, base_w, leader);
+            rank[r] = base_w + (unsigned int)__popc(peers & ((1u << lane) - 1u));
+        }
     }
     __syncthreads();
-    if (cnt[threadIdx.x]) base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], cnt[threadIdx.x]);
+    if (cnt[tid]) base[tid] = pre[tid] + atomicAdd(&fill[tid], cnt[tid]);
     __syncthreads();
-    if (p < n) perm[base[key] + rank] = (int)p;
+#pragma unroll
+    for (int r = 0; r < KEY_PER_THREAD; ++r) {
+        const long long p = ((long long)blockIdx.x * KEY_PER_THREAD + r) * blockDim.x + tid;
+        if (p < n) perm[base[key[r]] + rank[r]] = (int)p;
+    }
 }
 
 // ln x_p(k) on the uniform k grid of igam_inv_tab (once per configuration)
@@ -1082,15 +1117,13 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
         }
         if (!ctx->perm_valid || ctx->perm_n != args.n) {
             CUDA_TRY(cudaMemsetAsync(ctx->d_hist, 0, sizeof(unsigned int) * 512, ctx->stream));
-            const unsigned blocks = (unsigned)((args.n + 255) / 256);
             const unsigned key_blocks = (unsigned)((args.n + 256 * KEY_PER_THREAD - 1) / (256 * KEY_PER_THREAD));
             void* kp[4] = {(void*)&ctx->dev, (void*)&args, (void*)&ctx->d_keys, (void*)&ctx->d_hist};
             CUDA_TRY(cudaLaunchKernel((const void*)regime_key_kernel, dim3(key_blocks), dim3(256), kp, 0, ctx->stream));
-            unsigned int* cursor = ctx->d_hist + 256;
-            regime_scan_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_hist, cursor);
-            regime_scatter_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_keys, cursor, ctx->d_perm, args.n);
+            unsigned int* fill = ctx->d_hist + 256;  // zeroed by the memset above
+            regime_scatter_kernel<<<key_blocks, 256, 0, ctx->stream>>>(ctx->d_keys, ctx->d_hist, fill, ctx->d_perm, args.n);
             CUDA_TRY(cudaGetLastError());
-            ctx->launches += 3;
+            ctx->launches += 2;
             ctx->perm_fresh = true;
             ctx->perm_n = args.n;
         }
