@@ -859,7 +859,7 @@ __global__ void __launch_bounds__(256) regime_key_kernel(const __grid_constant__
                         if (!(kk == kk)) kk = k_hi;
                     }
                     const float theta = mean / kk;
-                    const float a_top = kk + (float)(cfg.Mp[i] - 1);
+                    const float a_top = kk + (float)(cfg.M - 1);
                     const int ai = (int)fminf(fmaxf(a_top, 0.f), (float)(kSerA - 1));
                     const float ser_lim = slim[ai];
                     float X = (float)cfg.thr[i] / theta;

@@ -793,7 +793,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                                 F[t] = (mm < kEps) ? 0.0 : jl_min(mm, H);
                             }
                         tpp_s_terms<P>(cfg, i, mom[i], [&](int x, int y) -> double {
-                            if (x >= MP || y >= MP) return 0.0;  // beyond N_2d_ints (Coalescence.jl:213)
+                            if (x >= Mp || y >= Mp) return 0.0;  // beyond N_2d_ints (Coalescence.jl:213)
                             return (x <= y) ? F[tri_ct(x < MP ? x : 0, y < MP ? y : 0, MP)] : F[tri_ct(y < MP ? y : 0, x < MP ? x : 0, MP)];
                         }, s1, s2);
                     };
@@ -808,12 +808,14 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                             for (int pp = 0; pp < MP; ++pp) one[pp] = 1.0;
                             contract(mp_tag, F, one);
                         };
-                        if (Mp == M) finish_ln(std::integral_constant<int, M>{});
-                        else finish_ln(std::integral_constant<int, M - 1>{});
+                        finish_ln(std::integral_constant<int, M>{});
                     } else {
                         const double inv_th = 1.0 / th;
                         const double gk = (cfg.kind[i] == CLOUDY_GAMMA) ? gamma_shape(k) : 1.0;
-                        const double a_top = k + (double)(Mp - 1);
+                        // All M orders are carried even when N_2d_ints[i] = M - 1 (two adjacent 2-moment modes): the downward
+                        // recurrence from the higher top order gives the same lower orders, the unused top entries are masked in
+                        // `contract`, and the node loop exists once per mode instead of twice (code size)
+                        const double a_top = k + (double)(M - 1);
                         // threshold: run-constant, or this parcel's own percentile (compute_threshold, ParticleDistributions.jl:747-761)
                         double thr = cfg.thr[i];
                         OwnGrid og;
@@ -934,8 +936,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                             for (int pp = 1; pp < MP; ++pp) thp[pp] = thp[pp - 1] * th;
                             contract(mp_tag, F, thp);
                         };
-                        if (Mp == M) finish(std::integral_constant<int, M>{});
-                        else finish(std::integral_constant<int, M - 1>{});
+                        finish(std::integral_constant<int, M>{});
                     }
                     done = true;
                 }
