@@ -320,7 +320,7 @@ def run_b200(args):
                 "note": "achieved = nominal algorithmic flop model of SURVEY 8(d) (two exp + one incomplete gamma per node and integral "
                         "entry sharing none) x parcels / time; the kernel EXECUTES ~4x fewer FP64 instructions than that model (one exp per "
                         "node, Taylor evaluation of the shared incomplete gamma), so frac ~ 1 coexists with ~50% FP64-pipe utilisation "
-                        "(profiles/r01_tpp_kernel_c2_ncu_full_summary.txt); kernel_ms includes the 3 regime-sort launches of each step",
+                        "(profiles/r01_tpp_kernel_c2_ncu_full_summary.txt); kernel_ms includes the 2 regime-sort launches of each step",
                 "hbm": {"achieved": BYTES_PER_EVAL * n / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": BYTES_PER_EVAL * n / (k_ms * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
