@@ -118,7 +118,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -341,7 +341,7 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"first {ns} parcels of the same ensemble, {dt:.1f} s; C/OpenMP structure-faithful "
                                               "restatement of the Julia path (oracle/cloudy_oracle.c)"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -359,8 +359,26 @@ def ensure_built():
             time.sleep(2.0)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the one JSON line of the contract, on the process's real stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # Libraries may write to fd 1 (NCCL prints its version banner there when NCCL_DEBUG is set): everything except the
+    # result line goes to stderr.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ensure_built()
     if args.impl == "reference":
         run_reference(args)
