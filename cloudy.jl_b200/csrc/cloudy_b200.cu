@@ -807,8 +807,17 @@ __global__ void __launch_bounds__(256) nq_kernel(const __grid_constant__ DevConf
 // The key is only a scheduling hint, so the distribution parameters are rebuilt in single precision (the FP32 pipe is idle
 // in this library; FP64 divisions would make this kernel cost 6 % of a C2 step) and the block histogram is warp-aggregated.
 constexpr int KEY_PER_THREAD = 4;
+// The sort can be done tile by tile (SORT_TILE consecutive parcels, a multiple of 256 * KEY_PER_THREAD so that a block never
+// straddles two tiles): the thread-per-parcel kernel walks the order front to back, so the parcels in flight then come from
+// one or two tiles and the gather stays local (a gather over a whole 16 Mi-parcel C4 ensemble moves 26 GB through DRAM for
+// 2.4 GB of state: a 128-byte line per 8-byte moment).  Measured on B200 (tools/bench_configs.py, CLOUDY_SORT_TILE):
+//   C4 (9 slots, 16 Mi parcels): whole ensemble 55.0 ms, 4 Mi tiles 47.5, 2 Mi 45.8, 1 Mi 50.9, 256 Ki 83.9, 64 Ki 103
+//   C5 (5 slots, 64 Mi parcels): whole ensemble 31.9 ms (fused step 93.6), 4 Mi 32.2 (97.0), 2 Mi 32.4 (99.0), 1 Mi 32.7 (100.6)
+// Small tiles lose more to mixed warps at the many bucket boundaries than they gain; wide states gain from 2 Mi tiles,
+// narrow ones do not, so the default is 2 Mi parcels for states of 8 or more slots and the whole ensemble otherwise.
+constexpr long long SORT_TILE_WIDE = 2097152;
 __global__ void __launch_bounds__(256) regime_key_kernel(const __grid_constant__ DevConfig cfg, const KArgs args, unsigned char* __restrict__ keys,
-                                                         unsigned int* __restrict__ hist) {
+                                                         unsigned int* __restrict__ hist, const long long SORT_TILE) {
     __shared__ unsigned int sh[256];
     __shared__ unsigned char sdeg[kSerZ][kSerA];  // per-thread (divergent) lookups: shared memory, not the constant bank
     __shared__ float slim[kSerA];
@@ -891,13 +900,16 @@ __global__ void __launch_bounds__(256) regime_key_kernel(const __grid_constant__
         }
     }
     __syncthreads();
-    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+    const long long tile = ((long long)blockIdx.x * KEY_PER_THREAD * blockDim.x) / SORT_TILE;
+    if (sh[threadIdx.x]) atomicAdd(&hist[tile * 256 + threadIdx.x], sh[threadIdx.x]);
 }
 
-// Stable-per-block counting-sort scatter.  Every block rebuilds the exclusive prefix of the 256-bin histogram itself (no
-// separate scan launch) and reserves its slots per bin with one global atomic; `fill` starts at zero.
+// Stable-per-block counting-sort scatter within the block's tile.  Every block rebuilds the exclusive prefix of its tile's
+// 256-bin histogram itself (no separate scan launch) and reserves its slots per bin with one global atomic; `fill`
+// starts at zero; tile t owns positions [t SORT_TILE, (t+1) SORT_TILE) of the order.
 __global__ void __launch_bounds__(256) regime_scatter_kernel(const unsigned char* __restrict__ keys, const unsigned int* __restrict__ hist,
-                                                             unsigned int* __restrict__ fill, int* __restrict__ perm, long long n) {
+                                                             unsigned int* __restrict__ fill, int* __restrict__ perm, long long n,
+                                                             const long long SORT_TILE) {
     __shared__ unsigned int cnt[256];
     __shared__ unsigned int base[256];
     __shared__ unsigned int pre[256];
@@ -909,7 +921,10 @@ __global__ void __launch_bounds__(256) regime_scatter_kernel(const unsigned char
         const long long p = ((long long)blockIdx.x * KEY_PER_THREAD + r) * blockDim.x + tid;
         key[r] = (p < n) ? keys[p] : 0u;
     }
-    // exclusive prefix of the histogram (Hillis-Steele over the block)
+    const long long tile = ((long long)blockIdx.x * KEY_PER_THREAD * blockDim.x) / SORT_TILE;
+    hist += tile * 256;
+    fill += tile * 256;
+    // exclusive prefix of the tile's histogram (Hillis-Steele over the block)
     const unsigned int own = hist[tid];
     pre[tid] = own;
     __syncthreads();
@@ -944,7 +959,7 @@ __global__ void __launch_bounds__(256) regime_scatter_kernel(const unsigned char
 #pragma unroll
     for (int r = 0; r < KEY_PER_THREAD; ++r) {
         const long long p = ((long long)blockIdx.x * KEY_PER_THREAD + r) * blockDim.x + tid;
-        if (p < n) perm[base[key[r]] + rank[r]] = (int)p;
+        if (p < n) perm[tile * SORT_TILE + base[key[r]] + rank[r]] = (int)p;
     }
 }
 
@@ -1009,7 +1024,7 @@ struct cloudy_ctx {
     int sort_mode;         // regime sort of the parcel order before the thread-per-parcel kernel (0 off, 1 on)
     unsigned char* d_keys;
     int* d_perm;
-    unsigned int* d_hist;  // [0..256) histogram, [256..512) cursors
+    unsigned int* d_hist;  // per sort tile: 256-bin histograms, then 256 fill counters per tile
     long long sort_cap;
     bool perm_valid;       // d_perm may be reused (set by the stepper for stages 2 and 3 of a step)
     bool perm_fresh;       // a sort ran since the stepper last cleared this flag
@@ -1111,17 +1126,22 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
             ctx->d_keys = nullptr; ctx->d_perm = nullptr; ctx->sort_cap = 0;
             CUDA_TRY(cudaMalloc(&ctx->d_keys, (size_t)args.n));
             CUDA_TRY(cudaMalloc(&ctx->d_perm, sizeof(int) * (size_t)args.n));
-            if (!ctx->d_hist) CUDA_TRY(cudaMalloc(&ctx->d_hist, sizeof(unsigned int) * 512));
+            cudaFree(ctx->d_hist);
+            ctx->d_hist = nullptr;
+            CUDA_TRY(cudaMalloc(&ctx->d_hist, sizeof(unsigned int) * 512 * (size_t)((args.n + 256 * KEY_PER_THREAD - 1) / (256 * KEY_PER_THREAD))));
             ctx->sort_cap = args.n;
             ctx->perm_valid = false;
         }
         if (!ctx->perm_valid || ctx->perm_n != args.n) {
-            CUDA_TRY(cudaMemsetAsync(ctx->d_hist, 0, sizeof(unsigned int) * 512, ctx->stream));
+            long long SORT_TILE = (d.nslots >= 8) ? SORT_TILE_WIDE : (1LL << 40);
+            if (const char* e = getenv("CLOUDY_SORT_TILE")) SORT_TILE = std::max<long long>(1, atoll(e) / (256 * KEY_PER_THREAD)) * (256 * KEY_PER_THREAD);
+            const size_t n_tiles = (size_t)((args.n + SORT_TILE - 1) / SORT_TILE);
+            CUDA_TRY(cudaMemsetAsync(ctx->d_hist, 0, sizeof(unsigned int) * 512 * n_tiles, ctx->stream));
             const unsigned key_blocks = (unsigned)((args.n + 256 * KEY_PER_THREAD - 1) / (256 * KEY_PER_THREAD));
-            void* kp[4] = {(void*)&ctx->dev, (void*)&args, (void*)&ctx->d_keys, (void*)&ctx->d_hist};
+            void* kp[5] = {(void*)&ctx->dev, (void*)&args, (void*)&ctx->d_keys, (void*)&ctx->d_hist, (void*)&SORT_TILE};
             CUDA_TRY(cudaLaunchKernel((const void*)regime_key_kernel, dim3(key_blocks), dim3(256), kp, 0, ctx->stream));
-            unsigned int* fill = ctx->d_hist + 256;  // zeroed by the memset above
-            regime_scatter_kernel<<<key_blocks, 256, 0, ctx->stream>>>(ctx->d_keys, ctx->d_hist, fill, ctx->d_perm, args.n);
+            unsigned int* fill = ctx->d_hist + 256 * n_tiles;  // zeroed by the memset above
+            regime_scatter_kernel<<<key_blocks, 256, 0, ctx->stream>>>(ctx->d_keys, ctx->d_hist, fill, ctx->d_perm, args.n, SORT_TILE);
             CUDA_TRY(cudaGetLastError());
             ctx->launches += 2;
             ctx->perm_fresh = true;

@@ -347,9 +347,15 @@ def test_standard_N_q_batched(cb):
         assert np.all(np.abs(got[:, i] - ref) <= 1e-12 * np.array(scale)), (i, got[:, i], ref)
 
 
-def test_regime_sort_is_bit_identical(cb):
-    """the optional regime sort only reorders the work: tendencies and fused steps are bit-identical"""
+@pytest.mark.parametrize("tile", [None, "4096"])
+def test_regime_sort_is_bit_identical(cb, tile, monkeypatch):
+    """the optional regime sort only reorders the work: tendencies and fused steps are bit-identical, whether the order is
+    built over the whole ensemble or tile by tile (CLOUDY_SORT_TILE; several tiles plus a partial last one here)"""
     from cloudy_b200 import workloads as W
+    if tile is not None:
+        monkeypatch.setenv("CLOUDY_SORT_TILE", tile)
+    else:
+        monkeypatch.delenv("CLOUDY_SORT_TILE", raising=False)
     for gen, n, dt in ((W.c2_gamma_exp, 20000, 0.05), (W.c4_three_modes, 6000, 1e-5)):
         par, state = gen(n_parcels=n)
         model = cb.CoalescenceModel(par)
