@@ -667,7 +667,6 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
         sh.kdeg_m[tid] = (unsigned char)kk;
     }
     __syncthreads();
-    const double* myCtc = sCt + tid;
     double* myCt = sCt + tid;
 
     const long long n = args.n;
