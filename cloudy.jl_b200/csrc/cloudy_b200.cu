@@ -1025,6 +1025,7 @@ struct cloudy_ctx {
     unsigned char* d_keys;
     int* d_perm;
     unsigned int* d_hist;  // per sort tile: 256-bin histograms, then 256 fill counters per tile
+    size_t hist_tiles;     // tiles d_hist has room for
     long long sort_cap;
     bool perm_valid;       // d_perm may be reused (set by the stepper for stages 2 and 3 of a step)
     bool perm_fresh;       // a sort ran since the stepper last cleared this flag
@@ -1126,9 +1127,6 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
             ctx->d_keys = nullptr; ctx->d_perm = nullptr; ctx->sort_cap = 0;
             CUDA_TRY(cudaMalloc(&ctx->d_keys, (size_t)args.n));
             CUDA_TRY(cudaMalloc(&ctx->d_perm, sizeof(int) * (size_t)args.n));
-            cudaFree(ctx->d_hist);
-            ctx->d_hist = nullptr;
-            CUDA_TRY(cudaMalloc(&ctx->d_hist, sizeof(unsigned int) * 512 * (size_t)((args.n + 256 * KEY_PER_THREAD - 1) / (256 * KEY_PER_THREAD))));
             ctx->sort_cap = args.n;
             ctx->perm_valid = false;
         }
@@ -1136,6 +1134,14 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
             long long SORT_TILE = (d.nslots >= 8) ? SORT_TILE_WIDE : (1LL << 40);
             if (const char* e = getenv("CLOUDY_SORT_TILE")) SORT_TILE = std::max<long long>(1, atoll(e) / (256 * KEY_PER_THREAD)) * (256 * KEY_PER_THREAD);
             const size_t n_tiles = (size_t)((args.n + SORT_TILE - 1) / SORT_TILE);
+            if (ctx->hist_tiles < n_tiles) {  // 256 histogram bins + 256 fill counters per tile
+                cudaStreamSynchronize(ctx->stream);
+                cudaFree(ctx->d_hist);
+                ctx->d_hist = nullptr;
+                ctx->hist_tiles = 0;
+                CUDA_TRY(cudaMalloc(&ctx->d_hist, sizeof(unsigned int) * 512 * n_tiles));
+                ctx->hist_tiles = n_tiles;
+            }
             CUDA_TRY(cudaMemsetAsync(ctx->d_hist, 0, sizeof(unsigned int) * 512 * n_tiles, ctx->stream));
             const unsigned key_blocks = (unsigned)((args.n + 256 * KEY_PER_THREAD - 1) / (256 * KEY_PER_THREAD));
             void* kp[5] = {(void*)&ctx->dev, (void*)&args, (void*)&ctx->d_keys, (void*)&ctx->d_hist, (void*)&SORT_TILE};
