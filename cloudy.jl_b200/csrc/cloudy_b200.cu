@@ -689,11 +689,22 @@ __global__ void scalar_kernel(const ScalarArgs a) {
 // rainshaft_helpers.jl:74-77.  moment(dist, q+β) for q = 0,1,2 follows from the q = 0 value by Γ(x+1) = xΓ(x).
 __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevConfig cfg, const KArgs args) {
     for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < args.n; p += (long long)gridDim.x * blockDim.x) {
-        for (int i = 0; i < cfg.N; ++i) {
+        // every moment of the cell is requested before any arithmetic: the kernel is load-latency bound otherwise
+        double raw[MAXN][3];
+#pragma unroll
+        for (int i = 0; i < MAXN; ++i)
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                raw[i][q] = (i < cfg.N && q < cfg.nprog[i]) ? __ldg(args.u_in + (cfg.slot0[i] + q) * args.s_in + p * args.ps_in) : 0.0;
+#pragma unroll
+        for (int i = 0; i < MAXN; ++i) {
+            if (i >= cfg.N) break;
             const int s0 = cfg.slot0[i], np = cfg.nprog[i], kind = cfg.kind[i];
             double mn[3] = {0.0, 0.0, 0.0};
-            for (int q = 0; q < np; ++q) {
-                double v = args.u_in[(s0 + q) * args.s_in + p * args.ps_in];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                if (q >= np) break;
+                double v = raw[i][q];
                 v = (v < 0.0) ? 0.0 : v;  // rainshaft_helpers.jl:52
                 mn[q] = v / cfg.norm[s0 + q];
             }
