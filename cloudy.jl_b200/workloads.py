@@ -213,11 +213,13 @@ def three_modes_order2(n_parcels=256, seed=SEED0 + 49):
     return par, m * _norm_factors(NProgMoms, NORMS)
 
 
-def random_model(rng, N, P, kinds=None, n_parcels=64, finite_thresholds=True):
+def random_model(rng, N, P, kinds=None, n_parcels=64, finite_thresholds=True, moving=False):
     """A random but physically shaped configuration for fuzz tests: ``kinds`` per mode (default: random Exp/Gamma, last mode
     any of the four), symmetric random tensor with the magnitude pattern of a normalised kernel, thresholds increasing by mode."""
     if kinds is None:
-        kinds = [int(rng.choice([L.EXPONENTIAL, L.GAMMA, L.MONODISPERSE])) for _ in range(N - 1)] + \
+        # compute_threshold exists for Exponential and Gamma modes only (ParticleDistributions.jl:747-761)
+        inner = [L.EXPONENTIAL, L.GAMMA] if moving else [L.EXPONENTIAL, L.GAMMA, L.MONODISPERSE]
+        kinds = [int(rng.choice(inner)) for _ in range(N - 1)] + \
                 [int(rng.choice([L.EXPONENTIAL, L.GAMMA, L.MONODISPERSE, L.LOGNORMAL]))]
     ctor = {L.EXPONENTIAL: lambda: Exp(1.0, 1.0), L.GAMMA: lambda: Gam(1.0, 1.0, 1.0), L.MONODISPERSE: lambda: Mono(1.0, 1.0),
             L.LOGNORMAL: lambda: LogN(1.0, 0.0, 1.0)}
@@ -229,7 +231,12 @@ def random_model(rng, N, P, kinds=None, n_parcels=64, finite_thresholds=True):
             c[a, b] = c[b, a] = rng.uniform(0.2, 1.0) * 5e-3 * 10.0 ** (-2.5 * (a + b - 1)) if (a + b) > 0 else rng.uniform(0.0, 1e-3)
     scales = [0.1 * 30.0 ** i for i in range(N)]  # mean mass scale of mode i (normalised units)
     thr = tuple((5.0 * scales[i] if finite_thresholds and rng.random() < 0.85 else math.inf) if i < N - 1 else math.inf for i in range(N))
-    cd = CoalescenceData(CoalescenceTensor(c), NProgMoms, thr, (1.0, 1.0))
+    if moving:
+        from .coalescence import MovingThreshold
+        pct = tuple((float(rng.choice([0.5, 0.9, 0.97, 0.99])) if rng.random() < 0.85 else 1.0) if i < N - 1 else 1.0 for i in range(N))
+        cd = CoalescenceData(CoalescenceTensor(c), NProgMoms, pct, (1.0, 1.0), MovingThreshold())
+    else:
+        cd = CoalescenceData(CoalescenceTensor(c), NProgMoms, thr, (1.0, 1.0))
     par = ModelParameters(pdists=pd, coal_data=cd, NProgMoms=NProgMoms, norms=(1.0, 1.0), dt=1.0)
     cols = []
     for i, k in enumerate(kinds):

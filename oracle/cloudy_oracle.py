@@ -373,7 +373,8 @@ def make_coalescence_data(kernel, NProgMoms: Sequence[int], dist_thresholds: Seq
 # --------------------------------------------------------------------------------------
 def compute_threshold(d: Dist, percentile: float = 0.97, minx: float = 1e-18) -> float:
     if d.kind == EXPONENTIAL:
-        return max(-d.p1 * math.log(1 - percentile), minx)
+        # Julia's log(0.0) is -Inf (percentile 1 → infinite threshold); Python's math.log raises instead
+        return max(-d.p1 * (math.log(1 - percentile) if percentile < 1 else -math.inf), minx)
     if d.kind == GAMMA:
         return max(d.p1 * float(sp.gammaincinv(d.p2, percentile)), minx)
     raise TypeError("compute_threshold is defined for Exponential and Gamma only")

@@ -39,3 +39,20 @@ def test_random_configurations(N, P):
         a, b = outs[keys[0]], outs[keys[-1]]
         scale = np.abs(a).max(axis=1, keepdims=True) + 1e-300
         assert np.all(np.abs(a - b) <= 1e-9 * scale + 1e-7 * np.abs(a))
+
+
+@pytest.mark.parametrize("N,P", [sh for sh in TPP_SHAPES if sh[0] >= 2])
+def test_random_moving_threshold_configurations(N, P):
+    """MovingThreshold (Coalescence.jl:152-185) on every thread-per-parcel shape: random percentiles per mode, thresholds
+    on both sides of 1 (unit grid and per-parcel grid), against the oracle"""
+    import cloudy_b200 as cb
+    from cloudy_b200 import workloads as W
+    rng = np.random.default_rng(7000 + 10 * N + P)
+    for trial in range(2):
+        par, state = W.random_model(rng, N, P, n_parcels=96, moving=True)
+        opar = oracle_params(par)
+        got = cb.CoalescenceModel(par).coal_tendency_host(state)
+        for i in range(8):
+            ref, sc = O.rhs_coal(state[i], opar, return_scale=True)
+            ok, worst = tendency_close(got[i], ref, sc, 1e-9)
+            assert ok, (N, P, trial, [d.kind for d in par.pdists], par.coal_data.dist_thresholds, i, worst)
