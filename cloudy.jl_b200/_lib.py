@@ -55,12 +55,22 @@ SIGNATURES = {
     "cloudy_state_download": (_P, _P, _D, C.c_int64),
     "cloudy_state_device_ptr": (_P, C.POINTER(C.c_void_p), _I64, _I32),
     "cloudy_state_copy": (_P, _P, _P),
+    "cloudy_state_regime_sort": (_P, _P),
+    "cloudy_state_order": (_P, C.POINTER(C.c_void_p)),
+    "cloudy_set_resort_interval": (_P, C.c_int32),
+    "cloudy_sort_count": (_P, _I64),
     "cloudy_coal_tendency": (_P, _P, _P),
     "cloudy_sedimentation_flux": (_P, _P, _P),
     "cloudy_rainshaft_rhs": (_P, _P, _P),
     "cloudy_ssprk33_steps": (_P, _P, C.c_double, C.c_int32, C.c_int32),
     "cloudy_moment_sums_device": (_P, _P, C.c_void_p),
     "cloudy_moment_sums": (_P, _P, _D),
+    "cloudy_comm_unique_id": (C.c_void_p,),
+    "cloudy_comm_init": (_P, C.c_int32, C.c_int32, C.c_void_p),
+    "cloudy_comm_destroy": (_P,),
+    "cloudy_comm_info": (_P, _I32, _I32, _I32),
+    "cloudy_moment_sums_allreduce": (_P, _P, _D),
+    "cloudy_moment_sums_fetch": (_P, _D),
     "cloudy_cond_evap": (_P, _P, C.c_double, C.c_void_p, C.c_double, C.c_double, _P),
     "cloudy_standard_N_q": (_P, _P, C.c_double, C.c_int32, C.c_void_p),
     "cloudy_coal_tendency_host": (_P, _D, _D, C.c_int64),

@@ -143,8 +143,10 @@ def get_coal_ints(cs, pdists, coal_data: CoalescenceData, ts: ThresholdStyle = N
             raise ValueError("NProgMoms does not match the distributions")
     ctx = ctx or default_context()
     kinds = tuple(d.kind for d in pdists)
-    # the 4-argument method (Coalescence.jl:152-157) reads coal_data.dist_thresholds as percentiles
-    moving = isinstance(ts, MovingThreshold) if ts is not None else isinstance(coal_data.threshold_style, MovingThreshold)
+    # Only the 4-argument method (Coalescence.jl:152-157) reads coal_data.dist_thresholds as percentiles; the 3-argument method
+    # (:115-150) ALWAYS treats them as mass thresholds, whatever style coal_data was built with (the reference's
+    # CoalescenceData does not even store the style).
+    moving = isinstance(ts, MovingThreshold)
     cfg = build_config(kinds, coal_data, norms=(1.0, 1.0), moving=moving)
     apply_config(ctx, cfg, key=("coal_ints", coal_data.uid, kinds, moving))
     params = np.zeros((coal_data.N, 3))

@@ -41,6 +41,15 @@ class Context:
         """0/False off, 1/True always, 2 auto (default)"""
         L.check(self._lib.cloudy_set_regime_sort(self.handle, int(mode)))
 
+    def set_resort_interval(self, steps: int):
+        """fused time steps between two refreshes of a resident ensemble's regime order (default 10)"""
+        L.check(self._lib.cloudy_set_resort_interval(self.handle, int(steps)))
+
+    def sort_count(self) -> int:
+        v = C.c_int64()
+        L.check(self._lib.cloudy_sort_count(self.handle, C.byref(v)))
+        return v.value
+
     def launch_count(self) -> int:
         v = C.c_int64()
         L.check(self._lib.cloudy_launch_count(self.handle, C.byref(v)))

@@ -17,6 +17,7 @@
 // from the downward recurrence gamma(a,z) = (gamma(a+1,z) + z^a e^-z)/a.  The polynomial-kernel
 // contraction (Q/R/S) runs one output moment per lane from shared memory.  FP64 CUDA cores only.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -30,6 +31,7 @@
 #include "../../include/cloudy_b200.h"
 #include "common.cuh"
 #include "tpp_kernel.cuh"
+#include "regime_sort.cuh"
 
 namespace cloudy {
 
@@ -746,6 +748,7 @@ struct AuxArgs {
     int normalized;    // N_q: rebuild distributions from moments / norms (1) or from the raw moments (0)
     double s, xi_n, rho_l, cutoff;
     const double* d_s;  // per-parcel supersaturation (optional)
+    const int* order;   // regime-ordered ensemble: original parcel index of every position (nullptr = identity)
 };
 
 __device__ inline ModeParams aux_params(const DevConfig& cfg, const AuxArgs& a, int i, long long p, bool normalise) {
@@ -766,7 +769,7 @@ __device__ inline ModeParams aux_params(const DevConfig& cfg, const AuxArgs& a, 
 __global__ void __launch_bounds__(256) cond_evap_kernel(const __grid_constant__ DevConfig cfg, const AuxArgs a) {
     const double geom = pow(4.0 * M_PI / 3.0, 2.0 / 3.0) / pow(a.rho_l, 1.0 / 3.0);
     for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < a.n; p += (long long)gridDim.x * blockDim.x) {
-        const double s = a.d_s ? a.d_s[p] : a.s;
+        const double s = a.d_s ? a.d_s[a.order ? (long long)a.order[p] : p] : a.s;  // d_s is indexed by parcel
         for (int i = 0; i < cfg.N; ++i) {
             const int s0 = cfg.slot0[i], np = cfg.nprog[i], kind = cfg.kind[i];
             const ModeParams mp = aux_params(cfg, a, i, p, true);
@@ -803,10 +806,11 @@ __global__ void __launch_bounds__(256) nq_kernel(const __grid_constant__ DevConf
             nr += moment_real(kind, mp.n, mp.a, mp.b, 0.0) - p0;
             mr += moment_real(kind, mp.n, mp.a, mp.b, 1.0) - p1;
         }
-        a.out[0 * a.s_out + p] = nl;
-        a.out[1 * a.s_out + p] = nr;
-        a.out[2 * a.s_out + p] = ml;
-        a.out[3 * a.s_out + p] = mr;
+        const long long o = a.order ? (long long)a.order[p] : p;
+        a.out[0 * a.s_out + o] = nl;
+        a.out[1 * a.s_out + o] = nr;
+        a.out[2 * a.s_out + o] = ml;
+        a.out[3 * a.s_out + o] = mr;
     }
 }
 
@@ -827,8 +831,12 @@ constexpr int KEY_PER_THREAD = 4;
 // Small tiles lose more to mixed warps at the many bucket boundaries than they gain; wide states gain from 2 Mi tiles,
 // narrow ones do not, so the default is 2 Mi parcels for states of 8 or more slots and the whole ensemble otherwise.
 constexpr long long SORT_TILE_WIDE = 2097152;
+// blockhist != nullptr selects the stable data sort of regime_sort.cuh: the block adds its histogram to
+// blockhist[bin][blockIdx.x / SORT_ROUNDS] and to totals[bin] (integer atomics on distinct counters: the result does not
+// depend on the order of arrival) instead of the per-tile histogram of the permutation sort.
 __global__ void __launch_bounds__(256) regime_key_kernel(const __grid_constant__ DevConfig cfg, const KArgs args, unsigned char* __restrict__ keys,
-                                                         unsigned int* __restrict__ hist, const long long SORT_TILE) {
+                                                         unsigned int* __restrict__ hist, const long long SORT_TILE,
+                                                         unsigned int* __restrict__ blockhist, unsigned int* __restrict__ totals, const int nblocks) {
     __shared__ unsigned int sh[256];
     __shared__ unsigned char sdeg[kSerZ][kSerA];  // per-thread (divergent) lookups: shared memory, not the constant bank
     __shared__ float slim[kSerA];
@@ -911,6 +919,13 @@ __global__ void __launch_bounds__(256) regime_key_kernel(const __grid_constant__
         }
     }
     __syncthreads();
+    if (blockhist != nullptr) {
+        if (sh[threadIdx.x]) {
+            atomicAdd(&blockhist[(size_t)threadIdx.x * nblocks + blockIdx.x / SORT_ROUNDS], sh[threadIdx.x]);
+            atomicAdd(&totals[threadIdx.x], sh[threadIdx.x]);
+        }
+        return;
+    }
     const long long tile = ((long long)blockIdx.x * KEY_PER_THREAD * blockDim.x) / SORT_TILE;
     if (sh[threadIdx.x]) atomicAdd(&hist[tile * 256 + threadIdx.x], sh[threadIdx.x]);
 }
@@ -980,14 +995,20 @@ __global__ void xp_table_kernel(double p, double k0, double h, int n, double* __
     if (i < n) out[i] = log(igam_inv(k0 + (double)i * h, p));
 }
 
-// FP64 peak: independent FMA chains
+// FP64 peak: 16 independent FMA chains per thread, the loop unrolled 4x (64 DFMA per branch)
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
-    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    double x[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = threadIdx.x * 1e-3 + j;
+#pragma unroll 4
     for (int i = 0; i < iters; ++i) {
-        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = fma(x[j], a, b);
     }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sum += x[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = sum;
 }
 
 }  // namespace cloudy
@@ -1008,11 +1029,21 @@ static int fail(int code, const std::string& msg) {
         if (_e != cudaSuccess) return fail(CLOUDY_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
+// order of a regime-sorted ensemble: d[i] = original parcel index of position i.  Shared between states that hold the same
+// parcels in the same order (a tendency inherits the order of the state it was evaluated at); reference counted.
+struct OrderBuf {
+    int* d;
+    long long n;
+    int refs;
+};
+
 struct cloudy_state {
     cloudy_ctx* ctx;
     double* d;
     long long n, stride;
     int nslots;
+    OrderBuf* order;   // nullptr: position == parcel index
+    int sort_age;      // fused time steps since the order was built
 };
 
 struct cloudy_ctx {
@@ -1041,6 +1072,22 @@ struct cloudy_ctx {
     bool perm_valid;       // d_perm may be reused (set by the stepper for stages 2 and 3 of a step)
     bool perm_fresh;       // a sort ran since the stepper last cleared this flag
     long long perm_n;      // ensemble size d_perm was computed for
+    // stable data sort (regime_sort.cuh)
+    unsigned int* d_blockhist;       // [256][nblocks] per-block histograms, then 256 bin totals
+    size_t blockhist_cap;            // in unsigned ints
+    cloudy_state* sort_scratch;      // destination of a state's data sort (buffers are swapped afterwards)
+    std::vector<OrderBuf*>* order_pool;  // released order buffers, reused by size
+    int resort_interval;             // fused steps between two sorts of a resident ensemble
+    int64_t sorts;                   // data sorts performed so far
+    // conservation all-reduce (NCCL, bound at run time with dlopen: the library has no link-time NCCL dependency)
+    void* nccl_comm;                 // ncclComm_t
+    int comm_size, comm_rank;
+    cudaStream_t s_comm;             // side stream: all-reduce + copy to the host overlap the next step
+    cudaEvent_t ev_sums, ev_comm;
+    double* d_sums;                  // [2][MAXSLOT]: local sums, all-reduced sums
+    double* h_sums;                  // pinned
+    bool sums_pending;
+    int sums_n;
     double* d_stage_aos;   // staging for upload/download
     // host-buffer pipeline (cloudy_coal_tendency_host): chunked H2D / kernel / D2H on three streams
     cudaStream_t s_h2d, s_d2h;
@@ -1131,7 +1178,7 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
     bool any_quad = false;
     for (int i = 0; i < d.N - 1; ++i) any_quad = any_quad || d.quad[i];
     const bool want_sort = ctx->sort_mode == 1 || (ctx->sort_mode == 2 && args.n >= 262144);  // auto: pays from ~2e5 parcels (measured)
-    if (want_sort && any_quad && !args.params_in && args.n >= 4096 && args.n < (1LL << 31)) {
+    if (want_sort && any_quad && !args.params_in && !args.presorted && args.n >= 4096 && args.n < (1LL << 31)) {
         if (ctx->sort_cap < args.n) {
             cudaStreamSynchronize(ctx->stream);
             cudaFree(ctx->d_keys); cudaFree(ctx->d_perm);
@@ -1155,7 +1202,10 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
             }
             CUDA_TRY(cudaMemsetAsync(ctx->d_hist, 0, sizeof(unsigned int) * 512 * n_tiles, ctx->stream));
             const unsigned key_blocks = (unsigned)((args.n + 256 * KEY_PER_THREAD - 1) / (256 * KEY_PER_THREAD));
-            void* kp[5] = {(void*)&ctx->dev, (void*)&args, (void*)&ctx->d_keys, (void*)&ctx->d_hist, (void*)&SORT_TILE};
+            unsigned int* no_hist = nullptr;
+            int no_blocks = 0;
+            void* kp[8] = {(void*)&ctx->dev, (void*)&args, (void*)&ctx->d_keys, (void*)&ctx->d_hist, (void*)&SORT_TILE,
+                           (void*)&no_hist, (void*)&no_hist, (void*)&no_blocks};
             CUDA_TRY(cudaLaunchKernel((const void*)regime_key_kernel, dim3(key_blocks), dim3(256), kp, 0, ctx->stream));
             unsigned int* fill = ctx->d_hist + 256 * n_tiles;  // zeroed by the memset above
             regime_scatter_kernel<<<key_blocks, 256, 0, ctx->stream>>>(ctx->d_keys, ctx->d_hist, fill, ctx->d_perm, args.n, SORT_TILE);
@@ -1214,6 +1264,181 @@ static int launch_rhs(cloudy_ctx* ctx, int model, const KArgs& args) {
     return CLOUDY_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// regime order of resident ensembles (regime_sort.cuh)
+// ------------------------------------------------------------------------------------------------
+static OrderBuf* order_acquire(cloudy_ctx* ctx, long long n) {
+    for (size_t i = 0; i < ctx->order_pool->size(); ++i)
+        if ((*ctx->order_pool)[i]->n == n) {
+            OrderBuf* b = (*ctx->order_pool)[i];
+            ctx->order_pool->erase(ctx->order_pool->begin() + i);
+            b->refs = 1;
+            return b;
+        }
+    OrderBuf* b = new OrderBuf();
+    b->n = n;
+    b->refs = 1;
+    b->d = nullptr;
+    if (cudaMalloc(&b->d, sizeof(int) * (size_t)std::max<long long>(n, 1)) != cudaSuccess) {
+        delete b;
+        return nullptr;
+    }
+    return b;
+}
+static void order_release(cloudy_ctx* ctx, OrderBuf* b) {
+    if (!b || --b->refs > 0) return;
+    // stream order makes the reuse safe: every kernel that reads the buffer was enqueued before the next sort writes it
+    if (ctx->order_pool->size() < 4) {
+        ctx->order_pool->push_back(b);
+    } else {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(b->d);
+        delete b;
+    }
+}
+static void state_set_order(cloudy_state* st, OrderBuf* o) {
+    if (st->order == o) return;
+    if (o) o->refs++;
+    order_release(st->ctx, st->order);
+    st->order = o;
+}
+
+// does the configuration profit from regime order, and is the ensemble large enough to pay for the sort?
+static bool sort_wanted(const cloudy_ctx* ctx, long long n) {
+    const DevConfig& d = ctx->dev;
+    bool any_quad = false;
+    for (int i = 0; i < d.N - 1; ++i) any_quad = any_quad || d.quad[i];
+    const bool want = ctx->sort_mode == 1 || (ctx->sort_mode == 2 && n >= 262144);  // auto: pays from ~2e5 parcels (measured)
+    return want && any_quad && n >= 4096 && n < (1LL << 31);
+}
+// the thread-per-parcel kernel will run for this model (the lane-cooperative kernel gains nothing from the order)
+static bool tpp_selected(const cloudy_ctx* ctx, int model) {
+    const bool moving = ctx->dev.thr_style == CLOUDY_MOVING_THRESHOLD;
+    const bool need_tpp = moving || ctx->dev.ln_thr[0] || ctx->dev.ln_thr[1] || ctx->dev.ln_thr[2];
+    if (!(ctx->lanes <= 1 || need_tpp)) return false;
+    return tpp_lookup(ctx->dev.N, ctx->dev.P, model == CLOUDY_MODEL_RAINSHAFT ? MODEL_RAINSHAFT : (moving ? MODEL_BOX_MOVING : MODEL_BOX)) != nullptr;
+}
+
+// keys -> per-block histograms -> prefix -> scatter: `in` (order `order_in`, nullptr = identity) is copied to `out` in regime
+// order and `order_out` receives the composed order.  All on the context's stream, no host synchronisation.
+static int sort_buffer(cloudy_ctx* ctx, const double* in, double* out, long long stride, int nslots, long long n, const int* order_in,
+                       int* order_out) {
+    const int nblocks = (int)((n + SORT_BLOCK_PARCELS - 1) / SORT_BLOCK_PARCELS);
+    const size_t need = (size_t)256 * nblocks + 256;
+    if (ctx->blockhist_cap < need) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->d_blockhist);
+        ctx->d_blockhist = nullptr;
+        ctx->blockhist_cap = 0;
+        CUDA_TRY(cudaMalloc(&ctx->d_blockhist, sizeof(unsigned int) * need));
+        ctx->blockhist_cap = need;
+    }
+    if (ctx->sort_cap < n) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->d_keys); cudaFree(ctx->d_perm);
+        ctx->d_keys = nullptr; ctx->d_perm = nullptr; ctx->sort_cap = 0;
+        CUDA_TRY(cudaMalloc(&ctx->d_keys, (size_t)n));
+        CUDA_TRY(cudaMalloc(&ctx->d_perm, sizeof(int) * (size_t)n));
+        ctx->sort_cap = n;
+        ctx->perm_valid = false;
+    }
+    CUDA_TRY(cudaMemsetAsync(ctx->d_blockhist, 0, sizeof(unsigned int) * need, ctx->stream));
+    unsigned int* totals = ctx->d_blockhist + (size_t)256 * nblocks;
+    KArgs a;
+    memset(&a, 0, sizeof(a));
+    a.u_in = in; a.s_in = stride; a.ps_in = 1; a.n = n;
+    const unsigned key_blocks = (unsigned)((n + 256 * KEY_PER_THREAD - 1) / (256 * KEY_PER_THREAD));
+    unsigned int* no_hist = nullptr;
+    long long no_tile = 1LL << 40;
+    void* kp[8] = {(void*)&ctx->dev, (void*)&a, (void*)&ctx->d_keys, (void*)&no_hist, (void*)&no_tile,
+                   (void*)&ctx->d_blockhist, (void*)&totals, (void*)&nblocks};
+    CUDA_TRY(cudaLaunchKernel((const void*)regime_key_kernel, dim3(key_blocks), dim3(256), kp, 0, ctx->stream));
+    sort_scan_kernel<<<256, SORT_THREADS, 0, ctx->stream>>>(ctx->d_blockhist, totals, nblocks);
+    CUDA_TRY(cudaGetLastError());
+    sort_scatter_kernel<<<nblocks, SORT_THREADS, 0, ctx->stream>>>(ctx->d_keys, ctx->d_blockhist, totals, nblocks, in, out, stride, nslots, n,
+                                                                    order_in, order_out);
+    CUDA_TRY(cudaGetLastError());
+    ctx->launches += 3;
+    ctx->sorts++;
+    return CLOUDY_OK;
+}
+
+// move a state's parcels into regime order (the device buffer is exchanged with the context's scratch ensemble)
+static int regime_sort_state(cloudy_ctx* ctx, cloudy_state* st) {
+    if (st->n == 0) return CLOUDY_OK;
+    if (!ctx->sort_scratch || ctx->sort_scratch->n != st->n) {
+        if (ctx->sort_scratch) { cloudy_state_destroy(ctx->sort_scratch); ctx->sort_scratch = nullptr; }
+        int rc = cloudy_state_create(ctx, st->n, &ctx->sort_scratch);
+        if (rc) return rc;
+    }
+    OrderBuf* o = order_acquire(ctx, st->n);
+    if (!o) return fail(CLOUDY_ERR_CUDA, "cudaMalloc(order) failed");
+    int rc = sort_buffer(ctx, st->d, ctx->sort_scratch->d, st->stride, st->nslots, st->n, st->order ? st->order->d : nullptr, o->d);
+    if (rc) { order_release(ctx, o); return rc; }
+    std::swap(st->d, ctx->sort_scratch->d);
+    order_release(ctx, st->order);
+    st->order = o;
+    st->sort_age = 0;
+    return CLOUDY_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// NCCL binding (dlopen): ncclUniqueId is 128 opaque bytes passed BY VALUE to ncclCommInitRank; ncclFloat64 = 8,
+// ncclSum = 0, ncclSuccess = 0 (nccl.h 2.x ABI)
+// ------------------------------------------------------------------------------------------------
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void* handle;
+    int (*GetUniqueId)(NcclId*);
+    int (*CommInitRank)(void**, int, NcclId, int);
+    int (*CommDestroy)(void*);
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    const char* (*GetErrorString)(int);
+    int (*GetVersion)(int*);
+};
+static NcclApi* nccl_api(std::string& err) {
+    static NcclApi api;
+    static bool tried = false, ok = false;
+    static std::string load_err;
+    if (!tried) {
+        tried = true;
+        const char* names[3] = {getenv("CLOUDY_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (int i = 0; i < 3 && !api.handle; ++i)
+            if (names[i] && names[i][0]) api.handle = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+        if (!api.handle) {
+            load_err = std::string("cannot load NCCL (libnccl.so.2): ") + (dlerror() ? dlerror() : "not found");
+        } else {
+            api.GetUniqueId = (int (*)(NcclId*))dlsym(api.handle, "ncclGetUniqueId");
+            api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(api.handle, "ncclCommInitRank");
+            api.CommDestroy = (int (*)(void*))dlsym(api.handle, "ncclCommDestroy");
+            api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.handle, "ncclAllReduce");
+            api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+            api.GetVersion = (int (*)(int*))dlsym(api.handle, "ncclGetVersion");
+            ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+            if (!ok) load_err = "libnccl is missing a required symbol";
+        }
+    }
+    if (!ok) { err = load_err; return nullptr; }
+    return &api;
+}
+#define NCCL_TRY(api, expr)                                                                              \
+    do {                                                                                                 \
+        int _r = (expr);                                                                                 \
+        if (_r != 0) return fail(CLOUDY_ERR_CUDA, std::string(#expr) + ": " + (api)->GetErrorString(_r)); \
+    } while (0)
+
+static int ensure_comm_buffers(cloudy_ctx* ctx) {
+    if (ctx->d_sums) return CLOUDY_OK;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->s_comm, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_sums, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc(&ctx->d_sums, sizeof(double) * 2 * MAXSLOT));
+    CUDA_TRY(cudaMallocHost(&ctx->h_sums, sizeof(double) * MAXSLOT));
+    return CLOUDY_OK;
+}
+
 extern "C" {
 
 const char* cloudy_last_error(void) { return g_last_error.c_str(); }
@@ -1238,6 +1463,8 @@ int cloudy_ctx_create(int device, void* stream, cloudy_ctx** out) {
     }
     c->lanes = 0;
     c->sort_mode = 2;
+    c->resort_interval = 10;
+    c->order_pool = new std::vector<OrderBuf*>();
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaMalloc(&c->d_err, sizeof(unsigned long long)));
     CUDA_TRY(cudaMemset(c->d_err, 0, sizeof(unsigned long long)));
@@ -1253,7 +1480,19 @@ int cloudy_ctx_destroy(cloudy_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 3; ++i)
         if (ctx->tmp[i]) cloudy_state_destroy(ctx->tmp[i]);
+    cloudy_comm_destroy(ctx);
+    if (ctx->d_sums) {
+        cudaStreamDestroy(ctx->s_comm);
+        cudaEventDestroy(ctx->ev_sums);
+        cudaEventDestroy(ctx->ev_comm);
+        cudaFree(ctx->d_sums);
+        cudaFreeHost(ctx->h_sums);
+    }
     if (ctx->flux) cloudy_state_destroy(ctx->flux);
+    if (ctx->sort_scratch) cloudy_state_destroy(ctx->sort_scratch);
+    for (OrderBuf* b : *ctx->order_pool) { cudaFree(b->d); delete b; }
+    delete ctx->order_pool;
+    cudaFree(ctx->d_blockhist);
     cudaFree(ctx->d_keys);
     cudaFree(ctx->d_perm);
     cudaFree(ctx->d_hist);
@@ -1490,29 +1729,38 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
             tab.resize(tab.size() + kXpN, 0.0);
         }
     }
-    cudaFree(ctx->d_tab);
-    ctx->d_tab = nullptr;
-    if (!tab.empty()) {
-        CUDA_TRY(cudaMalloc(&ctx->d_tab, sizeof(double) * tab.size()));
-        CUDA_TRY(cudaMemcpy(ctx->d_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
-    }
-    d.tab = ctx->d_tab;
-    for (int i = 0; i < N; ++i)
-        if (d.xp_off[i]) {
-            xp_table_kernel<<<(kXpN + 63) / 64, 64>>>(d.thr[i], d.xp_k0, 1.0 / d.xp_inv_h, kXpN, ctx->d_tab + d.xp_off[i]);
-            CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaDeviceSynchronize());
-        }
+    // every check that can still fail comes BEFORE the old configuration is touched: on any error the context keeps
+    // its previous, fully valid configuration (tables included)
     d.n_vel = cfg->n_vel;
     if (d.n_vel < 0 || d.n_vel > CLOUDY_MAX_VEL) return fail(CLOUDY_ERR_ARG, "n_vel out of range");
     for (int v = 0; v < d.n_vel; ++v) {
+        if (!(cfg->vel[v][1] >= 0.0 && cfg->vel[v][1] < 2.0)) return fail(CLOUDY_ERR_UNSUPPORTED, "terminal-velocity exponents must be in [0, 2)");
         d.velv[v] = cfg->vel[v][0] * pow(cfg->norms[1], cfg->vel[v][1]);  // rainshaft_helpers.jl:75
         d.velb[v] = cfg->vel[v][1];
         d.gam_b1[v] = tgamma(1.0 + cfg->vel[v][1]);
-        if (!(cfg->vel[v][1] >= 0.0 && cfg->vel[v][1] < 2.0)) return fail(CLOUDY_ERR_UNSUPPORTED, "terminal-velocity exponents must be in [0, 2)");
     }
     d.nz = cfg->nz > 0 ? cfg->nz : 1;
     d.dz = cfg->dz;
+    double* new_tab = nullptr;
+    if (!tab.empty()) {
+        CUDA_TRY(cudaMalloc(&new_tab, sizeof(double) * tab.size()));
+        cudaError_t e = cudaMemcpy(new_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice);
+        for (int i = 0; i < N && e == cudaSuccess; ++i)
+            if (d.xp_off[i]) {
+                xp_table_kernel<<<(kXpN + 63) / 64, 64>>>(d.thr[i], d.xp_k0, 1.0 / d.xp_inv_h, kXpN, new_tab + d.xp_off[i]);
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            }
+        if (e != cudaSuccess) {
+            cudaFree(new_tab);
+            return fail(CLOUDY_ERR_CUDA, std::string("cloudy_config_set(tables): ") + cudaGetErrorString(e));
+        }
+    }
+    // commit: nothing below can fail
+    cudaStreamSynchronize(ctx->stream);  // kernels of the previous configuration may still read the old tables
+    cudaFree(ctx->d_tab);
+    ctx->d_tab = new_tab;
+    d.tab = ctx->d_tab;
     ctx->mpmax = (mpmax == 0) ? 0 : (mpmax <= 4 ? 4 : (mpmax == 5 ? 5 : 7));
     ctx->dev = d;
     ctx->cfg = *cfg;
@@ -1536,6 +1784,8 @@ int cloudy_state_create(cloudy_ctx* ctx, int64_t n_parcels, cloudy_state** out) 
     s->stride = ((n_parcels + 31) / 32) * 32;  // 256-byte aligned slot columns
     if (s->stride == 0) s->stride = 32;
     s->d = nullptr;
+    s->order = nullptr;
+    s->sort_age = 0;
     cudaError_t e = cudaMalloc(&s->d, sizeof(double) * s->stride * s->nslots);
     if (e != cudaSuccess) {
         delete s;
@@ -1551,6 +1801,7 @@ int cloudy_state_destroy(cloudy_state* st) {
     cudaSetDevice(st->ctx->device);
     cudaStreamSynchronize(st->ctx->stream);
     cudaFree(st->d);
+    if (st->order && --st->order->refs == 0) { cudaFree(st->order->d); delete st->order; }
     delete st;
     return CLOUDY_OK;
 }
@@ -1582,6 +1833,8 @@ int cloudy_state_upload(cloudy_ctx* ctx, cloudy_state* st, const double* host, i
     const long long total = (long long)n_parcels * st->nslots;
     int rc = ensure_stage(ctx, total);
     if (rc) return rc;
+    state_set_order(st, nullptr);  // the host's order
+    st->sort_age = 0;
     CUDA_TRY(cudaMemcpyAsync(ctx->d_stage_aos, host, sizeof(double) * total, cudaMemcpyHostToDevice, ctx->stream));
     int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
     aos_to_soa_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_stage_aos, st->d, n_parcels, st->nslots, st->stride);
@@ -1599,7 +1852,10 @@ int cloudy_state_download(cloudy_ctx* ctx, const cloudy_state* st, double* host,
     int rc = ensure_stage(ctx, total);
     if (rc) return rc;
     int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-    soa_to_aos_kernel<<<blocks, 256, 0, ctx->stream>>>(st->d, ctx->d_stage_aos, n_parcels, st->nslots, st->stride);
+    if (st->order)  // regime-ordered ensemble: every parcel goes back to its original index
+        soa_to_aos_ordered_kernel<<<blocks, 256, 0, ctx->stream>>>(st->d, ctx->d_stage_aos, n_parcels, st->nslots, st->stride, st->order->d);
+    else
+        soa_to_aos_kernel<<<blocks, 256, 0, ctx->stream>>>(st->d, ctx->d_stage_aos, n_parcels, st->nslots, st->stride);
     CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     CUDA_TRY(cudaMemcpyAsync(host, ctx->d_stage_aos, sizeof(double) * total, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1611,6 +1867,8 @@ int cloudy_state_copy(cloudy_ctx* ctx, const cloudy_state* src, cloudy_state* ds
     if (!ctx || !src || !dst) return fail(CLOUDY_ERR_ARG, "NULL argument");
     if (src->n != dst->n || src->nslots != dst->nslots) return fail(CLOUDY_ERR_ARG, "state shapes differ");
     CUDA_TRY(cudaMemcpyAsync(dst->d, src->d, sizeof(double) * src->stride * src->nslots, cudaMemcpyDeviceToDevice, ctx->stream));
+    state_set_order(dst, src->order);
+    dst->sort_age = src->sort_age;
     return CLOUDY_OK;
 }
 
@@ -1639,8 +1897,16 @@ int cloudy_coal_tendency(cloudy_ctx* ctx, const cloudy_state* m, cloudy_state* d
     if (rc) return rc;
     if (m->n == 0) return CLOUDY_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
+    // large ensembles are kept in regime order: the first evaluation moves the parcels (cloudy_state_regime_sort), every
+    // later one reads and writes whole lines.  `m` is logically const — same parcels, same values, new positions.
+    if (!m->order && sort_wanted(ctx, m->n) && tpp_selected(ctx, CLOUDY_MODEL_BOX)) {
+        rc = regime_sort_state(ctx, const_cast<cloudy_state*>(m));
+        if (rc) return rc;
+    }
+    state_set_order(dm, m->order);
     KArgs a = base_args(ctx, m, dm);
     a.tend_only = 1;
+    a.presorted = 1;
     return launch_rhs(ctx, CLOUDY_MODEL_BOX, a);
 }
 
@@ -1649,6 +1915,7 @@ int cloudy_sedimentation_flux(cloudy_ctx* ctx, const cloudy_state* m, cloudy_sta
     if (rc) return rc;
     if (m->n == 0) return CLOUDY_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
+    state_set_order(flux, m->order);
     KArgs a = base_args(ctx, m, flux);
     a.tend_only = 1;
     a.flux_only = 1;
@@ -1661,7 +1928,9 @@ int cloudy_rainshaft_rhs(cloudy_ctx* ctx, cloudy_state* m, cloudy_state* dm) {
     if (m->n == 0) return CLOUDY_OK;
     if (m->n % ctx->dev.nz != 0) return fail(CLOUDY_ERR_ARG, "cell count is not a multiple of nz");
     if (!(ctx->dev.dz > 0)) return fail(CLOUDY_ERR_ARG, "dz must be positive");
+    if (m->order) return fail(CLOUDY_ERR_STATE, "the column model needs cells in column order; this state was regime-sorted (upload it again)");
     CUDA_TRY(cudaSetDevice(ctx->device));
+    state_set_order(dm, nullptr);
     KArgs a = base_args(ctx, m, dm);
     a.tend_only = 1;
     a.clip_back = m->d;
@@ -1703,15 +1972,30 @@ int cloudy_ssprk33_steps(cloudy_ctx* ctx, cloudy_state* u, double dt, int32_t n_
     double* t2 = ctx->tmp[1]->d;
     double* nxt = ctx->tmp[2]->d;
     const long long st = u->stride;  // all four share the stride (same n)
+    // box model: the ensemble is resident in regime order (regime_sort.cuh); the order is refreshed every
+    // `resort_interval` steps from the current state (a scheduling hint only: results do not depend on it)
+    const bool box = (model == CLOUDY_MODEL_BOX);
+    if (!box && u->order) return fail(CLOUDY_ERR_STATE, "the column model needs cells in column order; this state was regime-sorted (upload it again)");
+    const bool resident = box && sort_wanted(ctx, u->n) && tpp_selected(ctx, model);
     for (int step = 0; step < n_steps; ++step) {
+        if (resident && (!u->order || u->sort_age >= ctx->resort_interval)) {
+            OrderBuf* o = order_acquire(ctx, u->n);
+            if (!o) return fail(CLOUDY_ERR_CUDA, "cudaMalloc(order) failed");
+            if ((rc = sort_buffer(ctx, cur, nxt, st, u->nslots, u->n, u->order ? u->order->d : nullptr, o->d))) { order_release(ctx, o); return rc; }
+            std::swap(cur, nxt);
+            order_release(ctx, u->order);
+            u->order = o;
+            u->sort_age = 0;
+        }
         KArgs a;
         memset(&a, 0, sizeof(a));
         a.n = u->n; a.dt = dt; a.err_count = ctx->d_err;
         a.s_in = a.s_n = a.s_out = st;
         a.ps_in = a.ps_out = 1;
+        a.presorted = box ? 1 : 0;
         // stage 1: tmp = u + dt f(u)
         a.u_in = cur; a.u_n = nullptr; a.out = t1; a.cn = 0; a.ci = 1; a.cf = 1; a.div = 1;
-        ctx->perm_valid = false;  // new regime sort (if enabled) at the first stage, reused by stages 2 and 3
+        ctx->perm_valid = false;  // column model: new permutation sort (if enabled) at the first stage, reused by stages 2 and 3
         ctx->perm_fresh = false;
         if ((rc = launch_rhs(ctx, model, a))) return rc;
         ctx->perm_valid = ctx->perm_fresh;
@@ -1722,12 +2006,43 @@ int cloudy_ssprk33_steps(cloudy_ctx* ctx, cloudy_state* u, double dt, int32_t n_
         a.u_in = t2; a.u_n = cur; a.out = nxt; a.cn = 1; a.ci = 2; a.cf = 2; a.div = 3;
         if ((rc = launch_rhs(ctx, model, a))) return rc;
         std::swap(cur, nxt);
+        u->sort_age++;
     }
     ctx->perm_valid = false;
     if (cur != u->d) {
-        // odd number of swaps: `cur` is a work buffer; hand its storage to the caller's state
-        std::swap(u->d, ctx->tmp[2]->d);
+        // `cur` is a work buffer: hand its storage to the caller's state
+        if (cur == ctx->tmp[2]->d) std::swap(u->d, ctx->tmp[2]->d);
+        else return fail(CLOUDY_ERR_STATE, "internal: stepper buffers out of order");
     }
+    return CLOUDY_OK;
+}
+
+int cloudy_state_regime_sort(cloudy_ctx* ctx, cloudy_state* st) {
+    if (!ctx || !st) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (!ctx->configured) return fail(CLOUDY_ERR_STATE, "cloudy_config_set has not been called");
+    if (st->nslots != ctx->dev.nslots) return fail(CLOUDY_ERR_ARG, "state shape does not match the configuration");
+    if (ctx->dev.nz > 1) return fail(CLOUDY_ERR_STATE, "column states keep their cells in column order");
+    if (st->n >= (1LL << 31)) return fail(CLOUDY_ERR_UNSUPPORTED, "regime order supports fewer than 2^31 parcels per device");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return regime_sort_state(ctx, st);
+}
+
+int cloudy_state_order(const cloudy_state* st, const int32_t** d_order) {
+    if (!st || !d_order) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    *d_order = st->order ? st->order->d : nullptr;
+    return CLOUDY_OK;
+}
+
+int cloudy_set_resort_interval(cloudy_ctx* ctx, int32_t steps) {
+    if (!ctx) return fail(CLOUDY_ERR_ARG, "ctx is NULL");
+    if (steps < 1) return fail(CLOUDY_ERR_ARG, "the resort interval must be at least one step");
+    ctx->resort_interval = steps;
+    return CLOUDY_OK;
+}
+
+int cloudy_sort_count(cloudy_ctx* ctx, int64_t* out) {
+    if (!ctx || !out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    *out = ctx->sorts;
     return CLOUDY_OK;
 }
 
@@ -1748,6 +2063,106 @@ int cloudy_moment_sums(cloudy_ctx* ctx, const cloudy_state* u, double* host_out)
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(host_out, ctx->d_scratch, sizeof(double) * u->nslots, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return CLOUDY_OK;
+}
+
+
+// ---- multi-GPU: the path's only collective -------------------------------------------------------
+int cloudy_comm_unique_id(void* id_out) {
+    if (!id_out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    std::string err;
+    NcclApi* api = nccl_api(err);
+    if (!api) return fail(CLOUDY_ERR_UNSUPPORTED, err);
+    NcclId id;
+    NCCL_TRY(api, api->GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof(id));
+    return CLOUDY_OK;
+}
+
+int cloudy_comm_init(cloudy_ctx* ctx, int32_t n_ranks, int32_t rank, const void* unique_id) {
+    if (!ctx) return fail(CLOUDY_ERR_ARG, "ctx is NULL");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(CLOUDY_ERR_ARG, "invalid rank / n_ranks");
+    if (ctx->nccl_comm) return fail(CLOUDY_ERR_STATE, "the context already has a communicator");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc = ensure_comm_buffers(ctx);
+    if (rc) return rc;
+    ctx->comm_size = n_ranks;
+    ctx->comm_rank = rank;
+    if (n_ranks == 1) return CLOUDY_OK;  // nothing to exchange
+    if (!unique_id) return fail(CLOUDY_ERR_ARG, "unique_id is NULL");
+    std::string err;
+    NcclApi* api = nccl_api(err);
+    if (!api) return fail(CLOUDY_ERR_UNSUPPORTED, err);
+    NcclId id;
+    memcpy(&id, unique_id, sizeof(id));
+    NCCL_TRY(api, api->CommInitRank(&ctx->nccl_comm, n_ranks, id, rank));
+    return CLOUDY_OK;
+}
+
+int cloudy_comm_destroy(cloudy_ctx* ctx) {
+    if (!ctx) return fail(CLOUDY_ERR_ARG, "ctx is NULL");
+    if (ctx->nccl_comm) {
+        std::string err;
+        NcclApi* api = nccl_api(err);
+        cudaSetDevice(ctx->device);
+        if (ctx->s_comm) cudaStreamSynchronize(ctx->s_comm);
+        if (api) api->CommDestroy(ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    ctx->comm_size = 0;
+    ctx->comm_rank = 0;
+    return CLOUDY_OK;
+}
+
+int cloudy_comm_info(cloudy_ctx* ctx, int32_t* n_ranks, int32_t* rank, int32_t* nccl_version) {
+    if (!ctx) return fail(CLOUDY_ERR_ARG, "ctx is NULL");
+    if (n_ranks) *n_ranks = ctx->comm_size > 0 ? ctx->comm_size : 1;
+    if (rank) *rank = ctx->comm_rank;
+    if (nccl_version) {
+        *nccl_version = 0;
+        std::string err;
+        NcclApi* api = ctx->nccl_comm ? nccl_api(err) : nullptr;
+        if (api && api->GetVersion) api->GetVersion(nccl_version);
+    }
+    return CLOUDY_OK;
+}
+
+// Global per-slot sums: local two-pass reduction on the context's stream, then ncclAllReduce(sum, double, n_slots) and
+// the copy to pinned host memory on a side stream, so that the next step's kernels (already enqueued by the caller
+// after this returns with host_out == NULL) overlap the collective's latency.
+int cloudy_moment_sums_allreduce(cloudy_ctx* ctx, const cloudy_state* u, double* host_out) {
+    if (!ctx || !u) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int rc = ensure_comm_buffers(ctx);
+    if (rc) return rc;
+    if (ctx->sums_pending) CUDA_TRY(cudaStreamSynchronize(ctx->s_comm));  // the previous result is overwritten
+    if ((rc = cloudy_moment_sums_device(ctx, u, ctx->d_sums))) return rc;
+    CUDA_TRY(cudaEventRecord(ctx->ev_sums, ctx->stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->s_comm, ctx->ev_sums, 0));
+    const double* src = ctx->d_sums;
+    if (ctx->nccl_comm) {
+        std::string err;
+        NcclApi* api = nccl_api(err);
+        if (!api) return fail(CLOUDY_ERR_UNSUPPORTED, err);
+        NCCL_TRY(api, api->AllReduce(ctx->d_sums, ctx->d_sums + MAXSLOT, (size_t)u->nslots, 8 /*ncclFloat64*/, 0 /*ncclSum*/, ctx->nccl_comm,
+                                     ctx->s_comm));
+        src = ctx->d_sums + MAXSLOT;
+    }
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_sums, src, sizeof(double) * u->nslots, cudaMemcpyDeviceToHost, ctx->s_comm));
+    // (d_sums is rewritten by the next call only after s_comm has been synchronised: above, or in cloudy_moment_sums_fetch)
+    ctx->sums_pending = true;
+    ctx->sums_n = u->nslots;
+    if (host_out) return cloudy_moment_sums_fetch(ctx, host_out);
+    return CLOUDY_OK;
+}
+
+int cloudy_moment_sums_fetch(cloudy_ctx* ctx, double* host_out) {
+    if (!ctx || !host_out) return fail(CLOUDY_ERR_ARG, "NULL argument");
+    if (!ctx->sums_pending) return fail(CLOUDY_ERR_STATE, "no all-reduce is pending");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->s_comm));
+    memcpy(host_out, ctx->h_sums, sizeof(double) * ctx->sums_n);
+    ctx->sums_pending = false;
     return CLOUDY_OK;
 }
 
@@ -2003,6 +2418,7 @@ int cloudy_cond_evap(cloudy_ctx* ctx, const cloudy_state* m, double s, const dou
     if (rc) return rc;
     if (m->n == 0) return CLOUDY_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
+    state_set_order(dm, m->order);
     AuxArgs a;
     memset(&a, 0, sizeof(a));
     a.u_in = m->d; a.s_in = m->stride; a.n = m->n; a.out = dm->d; a.s_out = dm->stride;
@@ -2020,6 +2436,7 @@ int cloudy_standard_N_q(cloudy_ctx* ctx, const cloudy_state* m, double size_cuto
     memset(&a, 0, sizeof(a));
     a.u_in = m->d; a.s_in = m->stride; a.n = m->n; a.out = d_out; a.s_out = m->n;
     a.cutoff = size_cutoff; a.normalized = normalized;
+    a.order = m->order ? m->order->d : nullptr;  // results are indexed by parcel, not by position
     return launch_aux(ctx, (const void*)nq_kernel, a);
 }
 
@@ -2067,7 +2484,7 @@ int cloudy_get_standard_N_q_1(cloudy_ctx* ctx, int32_t n_modes, const int32_t* k
 int cloudy_measure_fp64_peak(cloudy_ctx* ctx, double* tflops) {
     if (!ctx || !tflops) return fail(CLOUDY_ERR_ARG, "NULL argument");
     CUDA_TRY(cudaSetDevice(ctx->device));
-    const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 15;
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 14;
     double* d = nullptr;
     CUDA_TRY(cudaMalloc(&d, sizeof(double) * blocks * threads));
     cudaEvent_t e0, e1;
@@ -2082,7 +2499,7 @@ int cloudy_measure_fp64_peak(cloudy_ctx* ctx, double* tflops) {
         CUDA_TRY(cudaEventSynchronize(e1));
         float ms = 0;
         CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-        double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+        double fl = 2.0 * 16.0 * (double)iters * blocks * threads;
         best = std::max(best, fl / (ms * 1e-3) / 1e12);
     }
     ctx->launches += 6;

@@ -64,6 +64,7 @@ struct KArgs {
     const int* perm;      // processing order (regime-sorted parcel indices) or nullptr for identity
     const double* flux;   // rainshaft: per-cell sedimentation flux (SoA like the state), written by flux_kernel
     long long s_flux;
+    int presorted;        // host side only: the ensemble is resident in regime order (or must keep its order): no permutation sort
 };
 
 enum { MODEL_BOX = 0, MODEL_RAINSHAFT = 1, MODEL_BOX_MOVING = 2 };

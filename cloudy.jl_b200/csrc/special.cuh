@@ -62,10 +62,16 @@ __device__ inline double simpson_weight(int j, int n_bins) {
     const int e = n_bins + 1;
     double w = 0.0;
     if (j >= 5 && j <= n_bins - 3) w += 48.0;
-    if (j == 1 || j == e) w += 17.0;
-    if (j == 2 || j == e - 1) w += 59.0;
-    if (j == 3 || j == e - 2) w += 43.0;
-    if (j == 4 || j == e - 3) w += 49.0;
+    // each end term counts on its own: for n_bins < 8 a node can be a member of two pairs (n_bins = 4: node 3 is both
+    // "3" and "e - 2" and weighs 86/48), exactly as the reference's sum does
+    if (j == 1) w += 17.0;
+    if (j == e) w += 17.0;
+    if (j == 2) w += 59.0;
+    if (j == e - 1) w += 59.0;
+    if (j == 3) w += 43.0;
+    if (j == e - 2) w += 43.0;
+    if (j == 4) w += 49.0;
+    if (j == e - 3) w += 49.0;
     return w;
 }
 

@@ -831,8 +831,13 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                             // the lower bound stays at 1e-5 and the grid is the parcel's own
                             own_grid = thr > 1.0 && !skip;
                             if (own_grid) {
-                                const double nbf = floor((double)cfg.bins_per_log_unit * log10(thr / 1e-5) + 1e-10);
-                                og.nb = (nbf >= 3.0 && nbf < 65536.0) ? (int)nbf : 3;
+                                // n_bins = floor(n_bins_per_log_unit * log10(x_th / x_lb)), the reference's formula literally
+                                // (ParticleDistributions.jl:580); a node count outside the supported range is counted as an
+                                // invalid parcel (cloudy_error_count) instead of being evaluated on a made-up grid
+                                const double nbf = floor((double)cfg.bins_per_log_unit * log10(thr / 1e-5));
+                                const bool nb_ok = nbf >= 3.0 && nbf < 65536.0;
+                                if (!nb_ok && live && args.err_count != nullptr) atomicAdd(args.err_count, 1ULL);
+                                og.nb = nb_ok ? (int)nbf : 3;
                                 og.dx = (log(thr) - (-11.512925464970229)) / (double)og.nb;  // log(1e-5)
                             }
                         }

@@ -41,6 +41,22 @@ class ParcelEnsemble:
         L.check(L.load().cloudy_state_device_ptr(self.handle, C.byref(p), None, None))
         return p.value
 
+    def regime_sort(self):
+        """Move the parcels into regime order now (cloudy_state_regime_sort); the state is logically unchanged."""
+        L.check(L.load().cloudy_state_regime_sort(self.ctx.handle, self.handle))
+        return self
+
+    def order(self):
+        """Original parcel index of every position (host copy), or None while position == parcel index."""
+        p = C.c_void_p()
+        L.check(L.load().cloudy_state_order(self.handle, C.byref(p)))
+        if not p.value:
+            return None
+        out = np.empty(self.n, dtype=np.int32)
+        self.ctx.sync()
+        _DeviceBuffer.memcpy_d2h(out, p.value, 4 * self.n)
+        return out
+
     def upload(self, host):
         a = np.ascontiguousarray(host, dtype=np.float64)
         if a.shape != (self.n, self.n_slots):
@@ -71,12 +87,17 @@ class _DeviceBuffer:
 
     _rt = None
 
-    def __init__(self, ctx, n):
+    @staticmethod
+    def _runtime():
         if _DeviceBuffer._rt is None:
             import ctypes.util
             import glob
             cands = glob.glob("/usr/local/cuda/lib64/libcudart.so*") + [ctypes.util.find_library("cudart") or "libcudart.so"]
             _DeviceBuffer._rt = C.CDLL(cands[0])
+        return _DeviceBuffer._rt
+
+    def __init__(self, ctx, n):
+        _DeviceBuffer._runtime()
         self.ctx = ctx
         self.n = int(n)
         p = C.c_void_p()
@@ -84,6 +105,13 @@ class _DeviceBuffer:
         if rc != 0:
             raise L.CloudyError(-2, f"cudaMalloc failed ({rc})")
         self.ptr = p.value
+
+    @staticmethod
+    def memcpy_d2h(out, dev_ptr, nbytes):
+        _DeviceBuffer._runtime()
+        rc = _DeviceBuffer._rt.cudaMemcpy(out.ctypes.data_as(C.c_void_p), C.c_void_p(dev_ptr), C.c_size_t(nbytes), C.c_int(2))
+        if rc != 0:
+            raise L.CloudyError(-2, f"cudaMemcpy failed ({rc})")
 
     def download(self, out):
         self.ctx.sync()
@@ -157,6 +185,21 @@ class CoalescenceModel:
     def moment_sums(self, u: ParcelEnsemble):
         out = np.zeros(self.n_slots)
         L.check(L.load().cloudy_moment_sums(self.ctx.handle, u.handle, L.dptr(out)))
+        return out
+
+    def moment_sums_allreduce(self, u: ParcelEnsemble, wait: bool = True):
+        """Per-slot sums over the parcels of ALL ranks (cloudy_moment_sums_allreduce: local reduction + NCCL all-reduce on a
+        side stream).  ``wait=False`` only enqueues; collect the result later with ``moment_sums_fetch``."""
+        if wait:
+            out = np.zeros(self.n_slots)
+            L.check(L.load().cloudy_moment_sums_allreduce(self.ctx.handle, u.handle, L.dptr(out)))
+            return out
+        L.check(L.load().cloudy_moment_sums_allreduce(self.ctx.handle, u.handle, None))
+        return None
+
+    def moment_sums_fetch(self):
+        out = np.zeros(self.n_slots)
+        L.check(L.load().cloudy_moment_sums_fetch(self.ctx.handle, L.dptr(out)))
         return out
 
     def moment_sums_device(self, u: ParcelEnsemble, d_out_ptr: int):

@@ -35,3 +35,31 @@ def total_mass(sums, NProgMoms) -> float:
         out += float(sums[s + 1])
         s += n
     return out
+
+
+def init_comm(ctx, rank: int = None, world: int = None, group=None):
+    """Create the context's NCCL communicator (cloudy_comm_init) with torch.distributed as the bootstrap: rank 0 draws the
+    unique id (cloudy_comm_unique_id) and broadcasts its 128 bytes through the already initialised process group (gloo or
+    nccl).  A Julia host would ship the same bytes with MPI.jl or a shared file."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib as L
+    if rank is None or world is None:
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            rank, world = 0, 1
+    buf = (C.c_char * 128)()
+    if world > 1:
+        if rank == 0:
+            L.check(L.load().cloudy_comm_unique_id(C.cast(buf, C.c_void_p)))
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device="cuda" if on_gpu else "cpu")
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().tolist())
+        C.memmove(buf, raw, 128)
+    L.check(L.load().cloudy_comm_init(ctx.handle, int(world), int(rank), C.cast(buf, C.c_void_p)))
+    return rank, world

@@ -99,12 +99,26 @@ int cloudy_launch_count(cloudy_ctx* ctx, int64_t* out);
 /* execution-shape knob: 0 = auto (thread-per-parcel kernel when the (n_modes, P) shape has an instance, else 8 lanes),
  * 1 = thread per parcel, 4/8/16/32 = that many lanes cooperating on one parcel's quadrature nodes */
 int cloudy_set_lanes(cloudy_ctx* ctx, int lanes);
-/* regime sort: before the thread-per-parcel kernel, order the parcels by series length and series / continued-fraction
- * regime so that warps are homogeneous (three small kernels; the order is reused by the stages of a fused step).
- * Results are bit-identical either way.  on = 0 off, 1 always, 2 auto (default: from 262144 parcels, where it pays). */
+/* regime sort: order the parcels by series length and series / continued-fraction regime so that warps are homogeneous
+ * (see "Regime order" below: box-model ensembles are moved physically and stay sorted; column states and the host-buffer
+ * pipeline walk a permutation instead).  Results are bit-identical either way.
+ * on = 0 off, 1 always, 2 auto (default: from 262144 parcels, where it pays). */
 int cloudy_set_regime_sort(cloudy_ctx* ctx, int on);
 
-/* ---- device state ---------------------------------------------------------------------------- */
+/* fused steps between two refreshes of a resident ensemble's regime order (default 10) */
+int cloudy_set_resort_interval(cloudy_ctx* ctx, int32_t steps);
+/* number of data sorts this context has performed (diagnostic; bench.py reports it) */
+int cloudy_sort_count(cloudy_ctx* ctx, int64_t* out);
+
+/* ---- device state ----------------------------------------------------------------------------
+ * Regime order.  Parcels are independent, so their POSITION in the device arrays is free.  For large box-model
+ * ensembles (regime sort mode on/auto) the library moves the parcels into "regime order" — parcels that need the same
+ * series length / continued-fraction regime sit next to each other, so that warps are homogeneous — and keeps them
+ * there: cloudy_coal_tendency sorts an unsorted input state once (its output inherits the order),
+ * cloudy_ssprk33_steps refreshes the order every cloudy_set_resort_interval() steps, cloudy_state_download undoes it,
+ * cloudy_state_upload resets it.  Results never depend on the order (bit-identical).  Only callers that read the raw
+ * device buffer (cloudy_state_device_ptr) see it: cloudy_state_order() returns the original parcel index of every
+ * position.  Column (rainshaft) states are never reordered. */
 int cloudy_state_create(cloudy_ctx* ctx, int64_t n_parcels, cloudy_state** out);
 int cloudy_state_destroy(cloudy_state* st);
 /* host AoS [n_parcels][n_slots] → device SoA, and back; async on the ctx stream when host is pinned */
@@ -113,6 +127,11 @@ int cloudy_state_download(cloudy_ctx* ctx, const cloudy_state* st, double* host,
 /* raw device pointer / stride (in doubles) of the SoA buffer, for zero-copy interop */
 int cloudy_state_device_ptr(const cloudy_state* st, double** dptr, int64_t* stride, int32_t* n_slots);
 int cloudy_state_copy(cloudy_ctx* ctx, const cloudy_state* src, cloudy_state* dst);
+/* move the parcels of a box-model state into regime order now (three kernels: keys, per-bin prefix, stable scatter of all
+ * slots; deterministic).  Logically the state is unchanged. */
+int cloudy_state_regime_sort(cloudy_ctx* ctx, cloudy_state* st);
+/* *d_order = DEVICE pointer to n int32 (original parcel index of position i), or NULL when position == parcel index */
+int cloudy_state_order(const cloudy_state* st, const int32_t** d_order);
 
 /* ---- batched hot path ------------------------------------------------------------------------ */
 /* dm = rhs_coal!(AnalyticalCoalStyle, dm, m, p, threshold_style) for every parcel.
@@ -125,13 +144,34 @@ int cloudy_sedimentation_flux(cloudy_ctx* ctx, const cloudy_state* m, cloudy_sta
  * reference (rainshaft_helpers.jl:52).  Cells are column-major: parcel index = column*nz + level. */
 int cloudy_rainshaft_rhs(cloudy_ctx* ctx, cloudy_state* m, cloudy_state* dm);
 /* n_steps of SSPRK33 (Shu-Osher form used by OrdinaryDiffEqSSPRK; call sites e.g.
- * box_gamma_mixture.jl:38, rainshaft_gamma_mixture.jl:49) with the RHS fused into each stage update. */
+ * box_gamma_mixture.jl:38, rainshaft_gamma_mixture.jl:49) with the RHS fused into each stage update.
+ * Column model: every stage output, the returned state included, is clipped at zero.  This is the reference's sequence,
+ * not a deviation: its right-hand side clips the array it is handed IN PLACE (rainshaft_helpers.jl:52), and
+ * OrdinaryDiffEq's SSPRK33 evaluates f(u_{n+1}) at the end of every step (the first-same-as-last derivative) before the
+ * state is saved, so every saved state of the reference has been clipped too. */
 int cloudy_ssprk33_steps(cloudy_ctx* ctx, cloudy_state* u, double dt, int32_t n_steps, int32_t model);
 /* per-slot sums over all parcels of this device (the conservation diagnostic, cf. moments_sum in
  * test/examples/utils/netcdf_helpers.jl:34-42).  d_out: DEVICE pointer to n_slots doubles (so the caller
  * can all-reduce it with NCCL without a host round trip). */
 int cloudy_moment_sums_device(cloudy_ctx* ctx, const cloudy_state* u, double* d_out);
 int cloudy_moment_sums(cloudy_ctx* ctx, const cloudy_state* u, double* host_out);
+/* ---- multi-GPU (one context per GPU, one process per GPU) ----------------------------------------
+ * Parcels / whole columns are block-partitioned over the ranks with no halo and no exchange; the path's only collective is
+ * the all-reduce of the <= 12 per-slot sums (the conservation diagnostic the reference computes serially: moments_sum,
+ * test/examples/utils/netcdf_helpers.jl:34-42).  NCCL is bound at run time (dlopen of libnccl.so.2, or $CLOUDY_NCCL_LIB).
+ *   rank 0:   cloudy_comm_unique_id(id)  -> ship the 128 bytes to the other ranks (MPI.jl / a file / torch.distributed)
+ *   all:      cloudy_comm_init(ctx, n_ranks, rank, id)                 (collective: ncclCommInitRank)
+ *   all:      cloudy_moment_sums_allreduce(ctx, u, out | NULL)         (collective)
+ * With host_out == NULL the call only enqueues (local reduction on the context's stream, ncclAllReduce + copy to pinned host
+ * memory on a side stream) and the result is collected later with cloudy_moment_sums_fetch, so the next step overlaps the
+ * collective.  A context without a communicator (or with n_ranks == 1) returns its local sums. */
+int cloudy_comm_unique_id(void* id_out /* 128 bytes */);
+int cloudy_comm_init(cloudy_ctx* ctx, int32_t n_ranks, int32_t rank, const void* unique_id /* 128 bytes */);
+int cloudy_comm_destroy(cloudy_ctx* ctx);
+int cloudy_comm_info(cloudy_ctx* ctx, int32_t* n_ranks, int32_t* rank, int32_t* nccl_version);
+int cloudy_moment_sums_allreduce(cloudy_ctx* ctx, const cloudy_state* u, double* host_out);
+int cloudy_moment_sums_fetch(cloudy_ctx* ctx, double* host_out);
+
 /* dm = rhs_condensation!(dm, m, p, s): get_cond_evap(pdists(m), s, xi / norms[2]^(2/3), rho_l) .* mom_norms for every parcel.
  * test/examples/utils/box_model_helpers.jl:55-67 → src/Sources/Condensation.jl:22-37.  d_s: optional DEVICE array of
  * per-parcel supersaturations (NULL → the scalar s for all parcels). */
