@@ -9,10 +9,25 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "liboracle.so")
 
 
+def _host_id() -> str:
+    """identifies the CPU the library was compiled for (-march=native): model name + ISA flags"""
+    import hashlib
+    try:
+        txt = open("/proc/cpuinfo").read()
+        keep = [l for l in txt.splitlines() if l.startswith(("model name", "flags"))][:2]
+        return hashlib.sha1("\n".join(keep).encode()).hexdigest()
+    except Exception:
+        return "unknown"
+
+
 def build(force=False):
     src = os.path.join(HERE, "cloudy_oracle.c")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
-        subprocess.run(["make", "-C", HERE] + (["-B"] if force else []), check=True, capture_output=True)
+    tag = LIB + ".host"
+    same_host = os.path.exists(tag) and open(tag).read().strip() == _host_id()
+    if force or not os.path.exists(LIB) or not same_host or os.path.getmtime(LIB) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(HERE, "Makefile"))):
+        subprocess.run(["make", "-C", HERE, "-B"], check=True, capture_output=True)
+        with open(tag, "w") as f:
+            f.write(_host_id())
     return LIB
 
 
@@ -22,9 +37,9 @@ _lib = None
 def load():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
-            build()
+        build()  # no-op when the library exists and was compiled on this host's CPU
         _lib = C.CDLL(LIB)
+        _lib.cloudy_oracle_build_flags.restype = C.c_char_p
         _lib.cloudy_oracle_rhs_coal_batch.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64, C.c_int]
         _lib.cloudy_oracle_rhs_coal_batch.restype = C.c_int
         _lib.cloudy_oracle_max_threads.restype = C.c_int
@@ -32,6 +47,10 @@ def load():
                                                             C.c_int, C.c_double, C.c_double]
         _lib.cloudy_oracle_moment_source_helper.restype = C.c_double
     return _lib
+
+
+def build_flags() -> str:
+    return load().cloudy_oracle_build_flags().decode()
 
 
 def max_threads() -> int:

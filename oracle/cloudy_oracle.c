@@ -226,6 +226,11 @@ int cloudy_oracle_rhs_coal_batch(const cloudy_config* cfg, const double* m, doub
     return status;
 }
 
+#ifndef CLOUDY_ORACLE_FLAGS
+#define CLOUDY_ORACLE_FLAGS "unknown"
+#endif
+const char* cloudy_oracle_build_flags(void) { return CLOUDY_ORACLE_FLAGS; }
+
 int cloudy_oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
