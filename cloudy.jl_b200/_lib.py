@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcloudy_b200.so")
+LIB_PATH = os.environ.get("CLOUDY_LIB") or os.path.join(HERE, "libcloudy_b200.so")  # CLOUDY_LIB: development variants (build.py)
 
 MAX_MODES, MAX_P, MAX_VEL, MAX_SLOTS, MAX_NODES = 4, 5, 4, 12, 512
 EXPONENTIAL, GAMMA, LOGNORMAL, MONODISPERSE = 0, 1, 2, 3

@@ -9,8 +9,11 @@ CSRC = os.path.join(HERE, "csrc")
 UNITS = ["cloudy_b200.cu"] + [f"tpp_inst_{g}.cu" for g in "ABCDEFGH"]
 HEADERS = [os.path.join(CSRC, h) for h in ("special.cuh", "common.cuh", "tpp_kernel.cuh", "tpp_instances.inc")] + \
           [os.path.join(os.path.dirname(HERE), "include", "cloudy_b200.h")]
-LIB = os.path.join(HERE, "libcloudy_b200.so")
-OBJDIR = os.path.join(CSRC, "build")
+# development variants: CLOUDY_DEV=<tag> builds libcloudy_b200_<tag>.so with the BASELINE shapes only (-DTPP_DEV_SHAPES) plus
+# the flags in CLOUDY_DEV_FLAGS; load it with CLOUDY_LIB=<path> (cloudy.jl_b200/_lib.py)
+DEV = os.environ.get("CLOUDY_DEV", "")
+LIB = os.path.join(HERE, f"libcloudy_b200_{DEV}.so" if DEV else "libcloudy_b200.so")
+OBJDIR = os.path.join(CSRC, f"build_{DEV}" if DEV else "build")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -37,7 +40,8 @@ def _stale(target, deps):
 
 def _compile(unit):
     src = os.path.join(CSRC, unit)
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-c", "-o", _obj(unit), src]
+    dev = (["-DTPP_DEV_SHAPES"] + os.environ.get("CLOUDY_DEV_FLAGS", "").split()) if DEV else []
+    cmd = [_nvcc()] + NVCC_FLAGS + dev + ["-c", "-o", _obj(unit), src]
     res = subprocess.run(cmd, capture_output=True, text=True)
     return unit, " ".join(cmd), res.returncode, res.stdout + res.stderr
 

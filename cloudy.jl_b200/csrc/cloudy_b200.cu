@@ -1216,7 +1216,8 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
         }
         args.perm = ctx->d_perm;
     }
-    size_t smem = sizeof(double) * (((size_t)d.tpp_total + 1) / 2 * 2 + (size_t)TPP_CT_ROWS * TPP_THREADS);
+    const size_t staged = (d.thr_style == CLOUDY_MOVING_THRESHOLD) ? (size_t)d.tpp_total : (size_t)d.tpp2_total;
+    size_t smem = sizeof(double) * ((staged + 1) / 2 * 2 + (size_t)tpp_ct_rows(d.thr_style == CLOUDY_MOVING_THRESHOLD ? MODEL_BOX_MOVING : MODEL_BOX) * TPP_THREADS);
     CUDA_TRY(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, TPP_THREADS, smem));
@@ -1586,6 +1587,8 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
                 }
     // grid tables
     std::vector<double> tab, tab2;  // tab: SoA tables of the lane-cooperative kernel; tab2: records / rules of the thread-per-parcel kernel
+    std::vector<double> tab3, kblk3;  // FixedThreshold thread-per-parcel kernels: aligned records, Taylor degree per node block
+    const int S2 = tpp_rec2_stride(P);
     int mpmax = 0;
     bool any_ln = false;
     for (int i = 0; i < N; ++i) {
@@ -1683,6 +1686,33 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
                 d.rec_near[i] = n_near;
                 d.rec_far[i] = n_far;
                 (void)R;
+                // FixedThreshold kernels: the same near nodes as (tmx, ln x + ln(x_th - x), w_0 .. w_P, padding) records of S2
+                // doubles with the Taylor degree of every block of tpp_npl(P) near nodes (= degree of the block's last node),
+                // then the far nodes padded to a multiple of TPP_NPLF with at least one zero-weight dummy at the very end (its
+                // slot evaluates the series at the Taylor centre, tpp_nodes_fixed2)
+                d.rec2_off[i] = (int)tab3.size();
+                d.kblk2_off[i] = (int)kblk3.size();
+                const double* r0 = tab2.data() + d.rec_off[i];
+                auto push2 = [&](const double* r, bool dummy) {
+                    tab3.push_back(r[REC_TMX]);
+                    tab3.push_back(r[REC_LSUM]);
+                    for (int p = 0; p < S2 - 2; ++p) tab3.push_back((p <= P && !dummy) ? r[REC_W + p] : 0.0);
+                };
+                for (int q = 0; q < n_near; ++q) {
+                    push2(r0 + (size_t)q * R, false);
+                    if ((q + 1) % tpp_npl(P) == 0) kblk3.push_back(r0[(size_t)q * R + REC_K]);
+                }
+                int n_far2 = 0;
+                for (int q = n_near; q < n_near + n_far; ++q) {
+                    const double* r = r0 + (size_t)q * R;
+                    bool zero_w = true;
+                    for (int p = 0; p < d.M; ++p) zero_w = zero_w && r[REC_W + p] == 0.0;
+                    if (q >= n_near + n_far - tpp_npl(P) && zero_w) continue;  // padding of the 3-node layout
+                    push2(r, false);
+                    ++n_far2;
+                }
+                do { push2(r0 + (size_t)(n_near + n_far - 1) * R, true); ++n_far2; } while (n_far2 % TPP_NPLF);
+                d.rec2_far[i] = n_far2;
             }
             mpmax = std::max(mpmax, d.Mp[i]);
         }
@@ -1718,6 +1748,20 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
     d.tpp_off = (int)tab.size();
     d.tpp_total = (int)tab2.size();
     tab.insert(tab.end(), tab2.begin(), tab2.end());
+    if (tab.size() & 1) tab.push_back(0.0);  // 16-byte alignment of the records below (cudaMalloc aligns the base)
+    d.tpp2_off = (int)tab.size();
+    d.gl2_off = 0;
+    if (any_ln) tab.insert(tab.end(), tab2.begin() + d.gl_off, tab2.begin() + d.gl_off + 2 * d.gl_n);  // 256 doubles: keeps the alignment
+    {
+        const int rec_base = (int)tab.size() - d.tpp2_off;
+        for (int i = 0; i < N; ++i) if (d.quad[i]) d.rec2_off[i] += rec_base;
+        tab.insert(tab.end(), tab3.begin(), tab3.end());
+        const int k_base = (int)tab.size() - d.tpp2_off;
+        for (int i = 0; i < N; ++i) if (d.quad[i]) d.kblk2_off[i] += k_base;
+        tab.insert(tab.end(), kblk3.begin(), kblk3.end());
+        if (tab.size() & 1) tab.push_back(0.0);
+    }
+    d.tpp2_total = (int)tab.size() - d.tpp2_off;
     // MovingThreshold: ln x_p(k) tables of the Gamma modes (not staged in shared memory; filled on the device below)
     d.xp_n = kXpN;
     d.xp_k0 = kXpK0;

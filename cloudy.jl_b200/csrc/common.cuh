@@ -34,7 +34,11 @@ struct DevConfig {
     int rec_off[MAXN], rec_near[MAXN], rec_far[MAXN];  // packed node records of the thread-per-parcel kernel (tpp_kernel.cuh)
     int xp_off[MAXN], xp_n;        // MovingThreshold: per Gamma mode, ln x_p(k) on a uniform k grid inside `tab` (special.cuh igam_inv_tab)
     int tab_total;                 // doubles of SoA grid tables the lane-cooperative kernel stages in shared memory
-    int tpp_off, tpp_total;        // region of `tab` the thread-per-parcel kernel stages (node records, Gauss-Legendre rule)
+    int tpp_off, tpp_total;        // region of `tab` the MovingThreshold thread-per-parcel kernels stage (node records, Gauss-Legendre rule)
+    // region the FixedThreshold thread-per-parcel kernels stage: [Gauss-Legendre rule | 16-byte aligned node records | block degrees]
+    int tpp2_off, tpp2_total, gl2_off;
+    int rec2_off[MAXN], kblk2_off[MAXN];  // per quadrature mode: records (tmx, lsum, w_0..w_P, pad) and Taylor degree per node block
+    int rec2_far[MAXN];                   // far nodes padded to a multiple of TPP_NPLF, at least one zero-weight dummy at the end
     int n_vel, nz;
     double c[MAXN][MAXN][MAXP][MAXP];
     double thr[MAXN];

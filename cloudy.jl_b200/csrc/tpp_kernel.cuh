@@ -24,8 +24,21 @@ constexpr int TPP_THREADS = 128;
 __host__ __device__ constexpr int tpp_npl(int P) { return (void)P, 3; }  // (2 for P >= 4 measured within noise: +4 % at 1 Mi, -4 % at 16 Mi parcels on C4)
 // resident blocks per SM the register allocation must allow (168 registers for 3 blocks of 128 threads): the small shapes
 // fit, the others take up to 255 registers and run 2 blocks
-__host__ __device__ constexpr int tpp_min_blocks(int N, int P, int model) { return (N * P <= 4 && N <= 3 && model != MODEL_BOX_MOVING) ? 3 : 2; }
-constexpr int TPP_CT_ROWS = 64;  // series coefficients c_0..c_63
+#ifndef TPP_MINB_SMALL
+#define TPP_MINB_SMALL 4
+#endif
+#ifndef TPP_MINB_LARGE
+#define TPP_MINB_LARGE 2
+#endif
+__host__ __device__ constexpr int tpp_min_blocks(int N, int P, int model) {
+    return model == MODEL_BOX_MOVING ? 2 : ((N * P <= 4 && N <= 3) ? TPP_MINB_SMALL : TPP_MINB_LARGE);
+}
+constexpr int TPP_CT_ROWS = 64;  // MovingThreshold instances: series coefficients c_0..c_63 (the Taylor coefficients overwrite them)
+// FixedThreshold instances keep only the Taylor coefficients t_0..t_26 in shared memory (the far-zone series runs on
+// coefficients generated on the fly), 216 bytes per thread
+constexpr int TPP_CT_ROWS_FIXED = 27;
+constexpr int TPP_NPLF = 5;       // far-zone nodes in flight per thread (FixedThreshold): one coefficient product serves five Horner chains
+__host__ __device__ constexpr int tpp_ct_rows(int model) { return model == 2 /*MODEL_BOX_MOVING*/ ? TPP_CT_ROWS : TPP_CT_ROWS_FIXED; }
 constexpr int TPP_TAYLOR_MAX = 26;  // Taylor coefficients t_0..t_26 of the near-node expansion
 
 __host__ __device__ constexpr int tri_ct(int p1, int p2, int MP) { return p1 * MP - (p1 * (p1 - 1)) / 2 + (p2 - p1); }
@@ -63,6 +76,9 @@ constexpr double kExpOffsetMin = -1.0e6;  // lower clamp of per-parcel exponent 
 // The host orders them [near nodes | far nodes], each zone padded to a multiple of tpp_npl(P) with zero-weight dummy
 // nodes, so the hot loop needs no index clamps and no validity selects.
 constexpr int REC_TMX = 0, REC_LSUM = 1, REC_ELL = 2, REC_X = 3, REC_K = 4, REC_W = 5;
+// FixedThreshold kernels: 16-byte aligned records (x_th - x_j, ln x_j + ln(x_th - x_j), w_j dx x_j^p for p = 0..P, padding to an
+// even count) read with 128-bit shared-memory loads; the Taylor degree of each node block sits in a separate array
+__host__ __device__ constexpr int tpp_rec2_stride(int P) { return 2 + ((P + 2) & ~1); }
 
 struct TableGrid {  // FixedThreshold (and MovingThreshold's unit grid): built on the host, broadcast from shared memory
     const double* rec;
@@ -375,138 +391,225 @@ __device__ __forceinline__ void tpp_cf_nodes(double (&acc)[MP * (MP + 1) / 2], c
     }
 }
 
-// FixedThreshold node loop: the far zone, the Taylor coefficients, the near zone and the continued-fraction nodes of
-// tpp_zone / tpp_taylor_coeffs / tpp_cf_nodes in ONE loop body (same arithmetic, same order; measured 15 % faster on C2
-// than the zone-by-zone form, which the MovingThreshold instances need to interleave two grids)
+// exp + accumulation of one block of NPL nodes (FixedThreshold node loop): y_p = g E z^p, top[p1] += w_p1 y_P z h,
+// Z[p1][p] += w_p1 y_p.  Inlined into the same basic block as the Horner evaluation of h, so that the scheduler interleaves
+// the NPL exponential chains with the NPL Horner chains (the two are independent).
+template <int MP, int P, int NPL>
+__device__ __forceinline__ void tpp_block_tail(double (&top)[P + 1], double (&Z)[(P + 1) * (P + 2) / 2], const double2* __restrict__ rb,
+                                               const double (&z)[NPL], const double (&h)[NPL], const double (&ls)[NPL],
+                                               const double k, const double e0, const double cf_lim, const double* __restrict__ exp_tab) {
+    constexpr int S2 = tpp_rec2_stride(P);
+    constexpr int P1 = P + 1;
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) {
+        const double gE = fast_exp(fma(k, ls[i], e0), exp_tab);  // g_j * E_j
+        const double hs = (z[i] < cf_lim) ? h[i] : 0.0;          // continued-fraction nodes are added by the rare loop
+        const double zh = z[i] * hs;
+        double w[P1 + 1];
+#pragma unroll
+        for (int q = 0; q < (S2 - 2) / 2; ++q) {
+            const double2 ww = rb[i * (S2 / 2) + 1 + q];
+            if (2 * q < P1 + 1) w[2 * q] = ww.x;
+            if (2 * q + 1 < P1 + 1) w[2 * q + 1] = ww.y;
+        }
+        double y[P1];
+        y[0] = gE;
+#pragma unroll
+        for (int p = 1; p < P1; ++p) y[p] = y[p - 1] * z[i];
+        const double ytop = y[P] * zh;
+#pragma unroll
+        for (int p1 = 0; p1 < P1; ++p1) {
+            top[p1] = fma(w[p1], ytop, top[p1]);
+#pragma unroll
+            for (int p = p1; p < P1; ++p) Z[tri_ct(p1, p, P1)] = fma(w[p1], y[p], Z[tri_ct(p1, p, P1)]);
+        }
+    }
+}
+
+// Near-zone Taylor polynomial sum_{m<=K} t_m r^m with a compile-time degree (no loop counter, immediate offsets).
+// -DTPP_HORNER_EVENODD splits it into its even and odd parts in r^2 (two chains per node): measured +2.5 % with 3 blocks/SM,
+// -1.5 % with 4 blocks/SM on C5 (the other warps already fill the DFMA latency), so the single chain is the default.
+template <int K, int NPL>
+__device__ __forceinline__ void tpp_taylor_horner(double (&h)[NPL], const double (&r)[NPL], const double* __restrict__ myCt) {
+#ifndef TPP_HORNER_EVENODD
+    const double t_top = myCt[K * TPP_THREADS];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) h[i] = t_top;
+#pragma unroll
+    for (int m = K - 1; m >= 0; --m) {
+        const double tm = myCt[m * TPP_THREADS];
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], r[i], tm);
+    }
+#else
+    constexpr int KE = (K % 2 == 0) ? K : K - 1;  // highest even / odd order
+    constexpr int KO = (K % 2 == 0) ? K - 1 : K;
+    double r2[NPL], he[NPL], ho[NPL];
+    const double te = myCt[KE * TPP_THREADS], to = myCt[KO * TPP_THREADS];
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) { r2[i] = r[i] * r[i]; he[i] = te; ho[i] = to; }
+#pragma unroll
+    for (int m = KE - 2; m >= 0; m -= 2) {
+        const double tm = myCt[m * TPP_THREADS];
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) he[i] = fma(he[i], r2[i], tm);
+    }
+#pragma unroll
+    for (int m = KO - 2; m >= 1; m -= 2) {
+        const double tm = myCt[m * TPP_THREADS];
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) ho[i] = fma(ho[i], r2[i], tm);
+    }
+#pragma unroll
+    for (int i = 0; i < NPL; ++i) h[i] = fma(ho[i], r[i], he[i]);
+#endif
+}
+
+struct FixedGrid {
+    const double* rec;    // shared memory: aligned records, [near | far]
+    const double* kblk;   // shared memory: Taylor degree per near block
+    int n_near, n_far;    // padded node counts
+    // natural-order SoA tables in global memory (continued-fraction nodes only): XJ[nb] ELL[nb] TMX[nb] LZ[nb] W[M][nb]
+    const double* soa;
+    int nb;
+};
+
+// FixedThreshold node loop.  Same quadrature, nodes and special-function evaluation as tpp_zone / tpp_cf_nodes above; what
+// differs is the bookkeeping of the T = MP(MP+1)/2 sums.  With v_p = g E h_p and h_p = (h_{p+1} + z^p)/(k+p) the sums obey
+//   acc[p1][p] = (acc[p1][p+1] + Z[p1][p]) / (k+p),   Z[p1][p] = sum_j w_j x_j^p1 (g E z^p)_j,   acc[p1][top] = sum_j w_j x_j^p1 (g E z^top S)_j
+// (all terms positive), so a node adds into Top[p1] and Z[p1][p] only (P+1 + (P+1)(P+2)/2 fused multiply-adds) and the
+// downward recurrence runs ONCE per parcel after the loop instead of once per node.
 template <int MP, int P>
-__device__ __forceinline__ void tpp_nodes_fixed(double (&acc)[MP * (MP + 1) / 2], const TableGrid grid, const double k,
-                                          const double inv_th, const double log_th, const double X, const double gam_top,
-                                          const double (&ia)[MP], double* __restrict__ myCt, const int deg_w, const int cfd_w,
-                                          const int cfd, const double a_top, const double ser_lim,
-                                          const double* __restrict__ exp_tab) {
+__device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2], const FixedGrid grid, const double k,
+                                                 const double inv_th, const double log_th, const double X, const double gam_top,
+                                                 const double (&ia)[MP], double* __restrict__ myCt, const int deg, const int cfd_w,
+                                                 const int cfd, const double a_top, const double ser_lim,
+                                                 const double* __restrict__ exp_tab) {
+    static_assert(MP == P + 2, "all M = P + 2 orders are carried");
     constexpr int T = MP * (MP + 1) / 2;
     constexpr int NPL = tpp_npl(P);
+    constexpr int S2 = tpp_rec2_stride(P);
+    constexpr int P1 = P + 1;              // p1 = 0..P (p1 <= p2 and p1 + p2 <= 2P), top order = P + 1
+    constexpr int NZ = P1 * (P1 + 1) / 2;  // Z[p1][p], p1 <= p <= P
+    double top[P1], Z[NZ];
 #pragma unroll
-    for (int t = 0; t < T; ++t) acc[t] = 0.0;
-    const int nb_w = grid.n_near + grid.n_far;  // loop bound
+    for (int i = 0; i < P1; ++i) top[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NZ; ++i) Z[i] = 0.0;
     const double e0 = fmax(fma(-2.0 * k, log_th, -X), kExpOffsetMin);  // exponent offset of g*E
     const double Xc = fmin(X, ser_lim - 0.5);       // Taylor centre (inside the series regime)
     const double rq = inv_th / Xc;                  // r = z/X_c - 1 = (x_th - x_j) rq - 1
     const bool capped = !(X <= ser_lim - 0.5);      // centre below x_th/θ: r does not vanish at the first nodes
     const bool warp_capped = __any_sync(0xffffffffu, capped);
     const bool warp_cf = __any_sync(0xffffffffu, !(X < ser_lim));  // any parcel of the warp with continued-fraction nodes
+    const double cf_lim = warp_cf ? ser_lim : INFINITY;
 
-    // near nodes come first in the padded tables; they are processed AFTER the far nodes (which need the c_n table)
-    int n_near_b = 0, jf = 0;
-    jf = grid.n_near;
-    n_near_b = jf / NPL;
-    const int n_far_b = (nb_w - jf + NPL - 1) / NPL;
-    for (int bt = 0; bt < n_far_b + n_near_b; ++bt) {
-        const bool near = bt >= n_far_b;
-        if (bt == n_far_b) {
-            // S(X_c) from the c_n table, then its Taylor coefficients into the same column
-            double s0 = myCt[deg_w * TPP_THREADS];
-            for (int n = deg_w - 1; n >= 0; --n) s0 = fma(s0, Xc, myCt[n * TPP_THREADS]);
-            const double Xa = Xc - a_top;
-            double tm1 = s0, tm = fma(Xa, s0, 1.0);
-            myCt[0] = tm1;
-            myCt[TPP_THREADS] = tm;
+    // ---- far nodes: S(z) = sum_n c_n z^n, c_n = 1/(a)_{n+1}, by Horner on SCALED coefficients generated on the fly:
+    //   Q_n = prod_{i=n+1..deg} (a+i) = c_n (a)_{deg+1},   R <- R z + Q_n,   S(z) = R_0 / (a)_{deg+1}
+    // (all terms positive).  One product Q_n serves the TPP_NPLF Horner chains in flight; the last slot of the last block is a
+    // zero-weight dummy whose argument is replaced by the Taylor centre X_c, which yields S(X_c) for the near zone.
+    // Each parcel runs its own degree `deg` (table kSeriesDeg2, truncation <= 2e-16): nothing depends on the warp-mates.
+    const int n_far_b = grid.n_far / TPP_NPLF;
+    double t0 = 0.0;       // S(X_c)
+    double inv_poch = 0.0; // 1/(a)_{deg+1}
+    for (int bt = 0; bt < n_far_b; ++bt) {
+        const double2* __restrict__ rb = reinterpret_cast<const double2*>(grid.rec + (grid.n_near + bt * TPP_NPLF) * S2);
+        double z[TPP_NPLF], R[TPP_NPLF], ls[TPP_NPLF];
 #pragma unroll
-            for (int m = 1; m < TPP_TAYLOR_MAX; ++m) {
-                const double tn = fma(Xa - (double)m, tm, Xc * tm1) * (1.0 / (double)(m + 1));
-                myCt[(m + 1) * TPP_THREADS] = tn;
-                tm1 = tm;
-                tm = tn;
-            }
+        for (int i = 0; i < TPP_NPLF; ++i) {
+            const double2 tl = rb[i * (S2 / 2)];
+            z[i] = tl.x * inv_th;
+            ls[i] = tl.y;
+            R[i] = 1.0;
         }
-        const int j0 = near ? (bt - n_far_b) * NPL : jf + bt * NPL;
-        double z[NPL], h[NPL];
+        const bool last = (bt == n_far_b - 1);
+        if (last) z[TPP_NPLF - 1] = Xc;
+        double Q = 1.0, aa = a_top + (double)deg;
+#pragma unroll 2
+        for (int n = deg - 1; n >= 0; --n) {
+            Q *= aa;      // Q_n = Q_{n+1} (a + n + 1)
+            aa -= 1.0;
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) z[i] = grid.o_tmx(j0 + i) * inv_th;  // (x_th - x_j)/θ
-        if (near) {
-            const int Kj = grid.o_degree(j0 + NPL - 1);  // node-only degree: the same for every parcel
-            double r[NPL];
+            for (int i = 0; i < TPP_NPLF; ++i) R[i] = fma(R[i], z[i], Q);
+        }
+        if (bt == 0) inv_poch = 1.0 / (Q * a_top);  // aa == a_top here
 #pragma unroll
-            for (int i = 0; i < NPL; ++i) r[i] = fma(grid.o_tmx(j0 + i), rq, -1.0);
-            if (!warp_capped) {
-                const double t_top = myCt[Kj * TPP_THREADS];
+        for (int i = 0; i < TPP_NPLF; ++i) R[i] *= inv_poch;
+        if (last) t0 = R[TPP_NPLF - 1];
+        tpp_block_tail<MP, P, TPP_NPLF>(top, Z, rb, z, R, ls, k, e0, cf_lim, exp_tab);
+    }
+    {
+        // Taylor coefficients of S about X_c into the parcel's shared-memory column:
+        //   t_1 = (X_c - a) t_0 + 1,  t_{m+1} = [(X_c - a - m) t_m + X_c t_{m-1}]/(m+1); the factors are formed off the dependent chain
+        const double Xa = Xc - a_top;
+        double tm1 = t0, tm = fma(Xa, t0, 1.0);
+        myCt[0] = tm1;
+        myCt[TPP_THREADS] = tm;
 #pragma unroll
-                for (int i = 0; i < NPL; ++i) h[i] = t_top;
-#pragma unroll 4
-                for (int m = Kj - 1; m >= 0; --m) {
-                    const double tm = myCt[m * TPP_THREADS];
+        for (int m = 1; m < TPP_TAYLOR_MAX; ++m) {
+            const double inv = 1.0 / (double)(m + 1);
+            const double tn = fma((Xa - (double)m) * inv, tm, (Xc * inv) * tm1);
+            myCt[(m + 1) * TPP_THREADS] = tn;
+            tm1 = tm;
+            tm = tn;
+        }
+    }
+    // ---- near nodes: Taylor polynomial about X_c, degree by node block ----
+    const int n_near_b = grid.n_near / NPL;
+    for (int bt = 0; bt < n_near_b; ++bt) {
+        const double2* __restrict__ rb = reinterpret_cast<const double2*>(grid.rec + bt * NPL * S2);
+        const int Kj = (int)grid.kblk[bt];  // node-only degree: the same for every parcel
+        if (!warp_capped) {
+            double z[NPL], h[NPL], ls[NPL], r[NPL];
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) {
+                const double2 tl = rb[i * (S2 / 2)];
+                r[i] = fma(tl.x, rq, -1.0);
+                z[i] = tl.x * inv_th;
+                ls[i] = tl.y;
+            }
+#define TPP_NEAR_CASE(KK) case KK: tpp_taylor_horner<KK, NPL>(h, r, myCt); break;
+            switch (Kj) {
+                TPP_NEAR_CASE(4) TPP_NEAR_CASE(5) TPP_NEAR_CASE(7) TPP_NEAR_CASE(9) TPP_NEAR_CASE(11) TPP_NEAR_CASE(14)
+                TPP_NEAR_CASE(16) TPP_NEAR_CASE(19) TPP_NEAR_CASE(22) TPP_NEAR_CASE(25)
+                default: tpp_taylor_horner<TPP_TAYLOR_MAX, NPL>(h, r, myCt); break;
+            }
+#undef TPP_NEAR_CASE
+            tpp_block_tail<MP, P, NPL>(top, Z, rb, z, h, ls, k, e0, cf_lim, exp_tab);
+        } else {
+            // a parcel whose centre is capped at the series limit sees |r| up to 0.1 at EVERY near node (r no longer
+            // vanishes with x_j/x_th): it takes the full degree; its warp-mates keep their own degree by predication
+            double z[NPL], h[NPL], ls[NPL], r[NPL];
+#pragma unroll
+            for (int i = 0; i < NPL; ++i) {
+                const double2 tl = rb[i * (S2 / 2)];
+                r[i] = fma(tl.x, rq, -1.0);
+                z[i] = tl.x * inv_th;
+                ls[i] = tl.y;
+                h[i] = 0.0;
+            }
+            const int Kown = capped ? TPP_TAYLOR_MAX : Kj;
+            for (int m = TPP_TAYLOR_MAX; m >= 0; --m) {
+                const double tm = myCt[m * TPP_THREADS];
+                if (m <= Kown) {
 #pragma unroll
                     for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], r[i], tm);
                 }
-            } else {
-                // a parcel whose centre is capped at the series limit sees |r| up to 0.1 at EVERY near node (r no longer
-                // vanishes with x_j/x_th): it takes the full degree; its warp-mates keep their own degree by predication
-                const int Kown = capped ? (TPP_TAYLOR_MAX - 1) : Kj;
-#pragma unroll
-                for (int i = 0; i < NPL; ++i) h[i] = 0.0;
-                for (int m = TPP_TAYLOR_MAX - 1; m >= 0; --m) {
-                    const double tm = myCt[m * TPP_THREADS];
-                    if (m <= Kown) {
-#pragma unroll
-                        for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], r[i], tm);
-                    }
-                }
             }
-        } else {
-            // Horner from the warp's largest degree; the own table is zero above the parcel's own degree, so the
-            // result does not depend on the neighbours
-            const double c_top = myCt[deg_w * TPP_THREADS];
-#pragma unroll
-            for (int i = 0; i < NPL; ++i) h[i] = c_top;
-            int n = deg_w - 1;
-            for (; n >= 3; n -= 4) {
-                const double c0 = myCt[n * TPP_THREADS], c1 = myCt[(n - 1) * TPP_THREADS], c2 = myCt[(n - 2) * TPP_THREADS],
-                             c3 = myCt[(n - 3) * TPP_THREADS];
-#pragma unroll
-                for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], z[i], c0);
-#pragma unroll
-                for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], z[i], c1);
-#pragma unroll
-                for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], z[i], c2);
-#pragma unroll
-                for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], z[i], c3);
-            }
-            for (; n >= 0; --n) {
-                const double c0 = myCt[n * TPP_THREADS];
-#pragma unroll
-                for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], z[i], c0);
-            }
+            tpp_block_tail<MP, P, tpp_npl(P)>(top, Z, rb, z, h, ls, k, e0, cf_lim, exp_tab);
         }
-        if (warp_cf) {  // continued-fraction nodes: added by the loop below (warp-uniform branch, rarely taken)
+    }
+    // downward recurrence of the sums; only entries with p1 + p2 <= 2P are ever read by the S terms
 #pragma unroll
-            for (int i = 0; i < NPL; ++i) h[i] = (z[i] < ser_lim) ? h[i] : 0.0;
-        }
+    for (int t = 0; t < T; ++t) acc[t] = 0.0;
 #pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-            const int j = j0 + i;
-            const double gE = fast_exp(fma(k, grid.o_log_sum(j), e0), exp_tab);  // g_j * E_j
-            const double hs = h[i];
-            // v_p = g E h_p with h_top = z^{MP-1} S, h_p = (h_{p+1} + z^p)/(k+p): carry g E z^p instead of z^p
-            double y[MP];
-            y[0] = gE;
+    for (int p1 = 0; p1 < P1; ++p1) {
+        double a = top[p1];
+        if (p1 + (MP - 1) <= 2 * P) acc[tri_ct(p1, MP - 1, MP)] = a;
 #pragma unroll
-            for (int p = 1; p < MP; ++p) y[p] = y[p - 1] * z[i];
-            double v[MP];
-            v[MP - 1] = y[MP - 1] * hs;
-#pragma unroll
-            for (int p = MP - 2; p >= 0; --p) v[p] = (v[p + 1] + y[p]) * ia[p];  // downward recurrence
-            double w[MP];
-            grid.template weights<MP>(j, 0.0, true, w);
-            int t = 0;
-#pragma unroll
-            for (int p1 = 0; p1 < MP; ++p1) {
-#pragma unroll
-                for (int p2 = p1; p2 < MP; ++p2) {
-                    // the S terms read F[a+c][b+m-c] with a,b < P, m <= 2: only entries with p1 + p2 <= 2P are ever used
-                    if (p1 + p2 <= 2 * P) acc[t] = fma(w[p1], v[p2], acc[t]);
-                    ++t;
-                }
-            }
+        for (int p = P; p >= p1; --p) {
+            a = (a + Z[tri_ct(p1, p, P1)]) * ia[p];
+            if (p1 + p <= 2 * P) acc[tri_ct(p1, p, MP)] = a;
         }
     }
 
@@ -516,12 +619,18 @@ __device__ __forceinline__ void tpp_nodes_fixed(double (&acc)[MP * (MP + 1) / 2]
         B[MP - 1] = 1.0;
 #pragma unroll
         for (int p = MP - 2; p >= 0; --p) B[p] = B[p + 1] * ia[p];
-        double G[MP];  // G[p1] = sum_j w_j dx x_j^p1 xi_j; the p2 dependence is the node-independent factor B[p2]
+        double G[P1];  // G[p1] = sum_j w_j dx x_j^p1 xi_j; the p2 dependence is the node-independent factor B[p2]
 #pragma unroll
-        for (int p = 0; p < MP; ++p) G[p] = 0.0;
+        for (int p = 0; p < P1; ++p) G[p] = 0.0;
+        const int nb = grid.nb;
+        const double* __restrict__ gx = grid.soa;
+        const double* __restrict__ gell = grid.soa + nb;
+        const double* __restrict__ gtmx = grid.soa + 2 * nb;
+        const double* __restrict__ glz = grid.soa + 3 * nb;
+        const double* __restrict__ gw = grid.soa + 4 * nb;
 #pragma unroll 1
-        for (int j = 0; j < nb_w; ++j) {
-            const double z = grid.o_tmx(j) * inv_th;
+        for (int j = 0; j < nb; ++j) {
+            const double z = __ldg(gtmx + j) * inv_th;
             const bool cf_j = !(z < ser_lim);
             if (!__any_sync(0xffffffffu, cf_j)) continue;
             const double zc = fmin(z, 256.0);  // beyond this the upper function is < 1e-80 of Gamma(a)
@@ -538,25 +647,22 @@ __device__ __forceinline__ void tpp_nodes_fixed(double (&acc)[MP * (MP + 1) / 2]
                 const double Qn = fma(bb, Qc, an * Qm);
                 Pm = Pc; Pc = Pn; Qm = Qc; Qc = Qn;
             }
-            const double gE = fast_exp(fma(k, grid.o_log_sum(j), e0), exp_tab);
-            const double g = fast_exp(fmax(fma(k, grid.ell(j) - log_th, -(grid.x(j) * inv_th)), kExpOffsetMin), exp_tab);  // (x_j/θ)^k e^{-x_j/θ}
+            const double ell = __ldg(gell + j);
+            const double gE = fast_exp(fma(k, ell + __ldg(glz + j), e0), exp_tab);
+            const double g = fast_exp(fmax(fma(k, ell - log_th, -(__ldg(gx + j) * inv_th)), kExpOffsetMin), exp_tab);  // (x_j/θ)^k e^{-x_j/θ}
             double zt = 1.0;
 #pragma unroll
             for (int p = 1; p < MP; ++p) zt *= z;
             double xi = fma(g, gam_top, -(gE * zt) * (Qc / Pc));
             xi = cf_j ? xi : 0.0;
-            double w[MP];
-            grid.template weights<MP>(j, 0.0, true, w);
 #pragma unroll
-            for (int p1 = 0; p1 < MP; ++p1) G[p1] = fma(w[p1], xi, G[p1]);
+            for (int p1 = 0; p1 < P1; ++p1) G[p1] = fma(__ldg(gw + p1 * nb + j), xi, G[p1]);
         }
-        int t = 0;
 #pragma unroll
-        for (int p1 = 0; p1 < MP; ++p1) {
+        for (int p1 = 0; p1 < P1; ++p1) {
 #pragma unroll
             for (int p2 = p1; p2 < MP; ++p2) {
-                if (p1 + p2 <= 2 * P) acc[t] = fma(G[p1], B[p2], acc[t]);
-                ++t;
+                if (p1 + p2 <= 2 * P) acc[tri_ct(p1, p2, MP)] = fma(G[p1], B[p2], acc[tri_ct(p1, p2, MP)]);
             }
         }
     }
@@ -648,12 +754,15 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
     constexpr int M = P + 2;
     constexpr bool RAIN = (MODEL == MODEL_RAINSHAFT);
     constexpr bool MOVING = (MODEL == MODEL_BOX_MOVING);  // MovingThreshold has its own instances (box model only, like the reference)
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     __shared__ TppShared sh;
     double* sTab = smem;
-    double* sCt = smem + ((cfg.tpp_total + 1) & ~1);
+    // staged tables: MovingThreshold instances use the packed records of TableGrid, the others the aligned records of FixedGrid
+    const int st_total = MOVING ? cfg.tpp_total : cfg.tpp2_total;
+    const int st_off = MOVING ? cfg.tpp_off : cfg.tpp2_off;
+    double* sCt = smem + ((st_total + 1) & ~1);
     const int tid = threadIdx.x;
-    for (int i = tid; i < cfg.tpp_total; i += TPP_THREADS) sTab[i] = cfg.tab[cfg.tpp_off + i];
+    for (int i = tid; i < st_total; i += TPP_THREADS) sTab[i] = cfg.tab[st_off + i];
     for (int i = tid; i < kSerZ * kSerA; i += TPP_THREADS) sh.deg[i / kSerA][i % kSerA] = kSeriesDeg2[i / kSerA][i % kSerA];
     if (tid < kSerA) { sh.cfd[tid] = kCfDepth[tid]; sh.serlim[tid] = kSeriesLimit[tid]; }
     for (int i = tid; i < TPP_EXP_TAB; i += TPP_THREADS) sh.exp32[i] = exp2((double)i / (double)TPP_EXP_TAB);
@@ -801,7 +910,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                         auto finish_ln = [&](auto mp_tag) {
                             constexpr int MP = decltype(mp_tag)::value;
                             double F[MP * (MP + 1) / 2];
-                            tpp_lognormal_H<MP>(F, sTab + cfg.gl_off, cfg.gl_n, nmd, th, k, cfg.thr[i]);
+                            tpp_lognormal_H<MP>(F, sTab + (MOVING ? cfg.gl_off : cfg.gl2_off), cfg.gl_n, nmd, th, k, cfg.thr[i]);
                             double one[MP];
 #pragma unroll
                             for (int pp = 0; pp < MP; ++pp) one[pp] = 1.0;
@@ -850,7 +959,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                         const int deg_w = __reduce_max_sync(0xffffffffu, deg);
                         const int cfd = sh.cfd[ai];
                         const int cfd_w = __reduce_max_sync(0xffffffffu, cfd);
-                        {   // c_n = 1/(a)_{n+1}: one division, then c_{n-1} = c_n (a+n)
+                        if constexpr (MOVING) {   // c_n = 1/(a)_{n+1}: one division, then c_{n-1} = c_n (a+n)
                             double pe = 1.0, po = 1.0;  // two independent product chains (even / odd factors)
                             for (int nn = 0; nn + 1 <= deg; nn += 2) {
                                 pe *= (a_top + (double)nn);
@@ -932,7 +1041,14 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                                     for (int p2 = p1; p2 < MP; ++p2) F[tri_ct(p1, p2, MP)] *= sc;
                                 }
                             } else {
-                                tpp_nodes_fixed<MP, P>(F, tg, k, inv_th, log(th), X, gam_top, ia, myCt, deg_w, cfd_w, cfd, a_top, ser_lim, sh.exp32);
+                                FixedGrid fg;
+                                fg.rec = sTab + cfg.rec2_off[i];
+                                fg.kblk = sTab + cfg.kblk2_off[i];
+                                fg.n_near = cfg.rec_near[i];
+                                fg.n_far = cfg.rec2_far[i];
+                                fg.soa = cfg.tab + cfg.tab_off[i];
+                                fg.nb = cfg.n_bins[i];
+                                tpp_nodes_fixed2<MP, P>(F, fg, k, inv_th, log(th), X, gam_top, ia, myCt, deg, cfd_w, cfd, a_top, ser_lim, sh.exp32);
                             }
                             double thp[MP];  // H = n^2 θ^{p2}/Γ(k)^2 * sum
                             thp[0] = pre0;
