@@ -6,12 +6,15 @@
          bench.py --gpus N --steps K --warmup W
   python bench.py --impl reference ...      # the reference's CPU path (oracle restatement) on the host cores
 
-A "step" is one evaluation of the coalescence right-hand side (rhs_coal!, box_model_helpers.jl:29-53) over every
-parcel of the rank's ensemble: BASELINE.json configs[1] — Gamma cloud + Exponential rain modes, linear (Golovin)
-kernel, 1,048,576 synthetic parcels per GPU (weak scaling: parcels shard with no exchange; every
---sums-every steps the per-slot moment sums are all-reduced with NCCL, the path's only collective).
+Workload = BASELINE.json configs[4] (C5, the configuration the scaling target is quoted on): the C2 ensemble — Gamma cloud +
+Exponential rain modes, linear (Golovin) kernel — with 67,108,864 synthetic parcels block-partitioned over the N GPUs
+(strong scaling: 2^26 / N parcels per GPU; N = 1 evaluates all 64 Mi parcels on one GPU), no exchange step.  A "step" is one
+evaluation of the coalescence right-hand side (rhs_coal!, box_model_helpers.jl:29-53) over every parcel of the rank's
+shard; every --sums-every steps the per-slot moment sums are all-reduced through the C ABI (cloudy_moment_sums_allreduce:
+two-pass device reduction + ncclAllReduce on a side stream), the path's only collective.
 """
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -26,10 +29,12 @@ import numpy as np
 
 METRIC = "coal-tendency evals/sec (parcels x RHS)"
 UNIT = "parcel-RHS/s"
-N_PARCELS = 1 << 20
+N_TOTAL = 1 << 26        # C5: 64 Mi parcels over all GPUs
+GEN_BLOCK = 1 << 23      # the generator runs on blocks of 8 Mi parcels (a 64 Mi shard repeats its block 8 times)
 # nominal algorithmic work per parcel-RHS for this workload (restated in DESIGN.md):
 FLOP_PER_EVAL = 1.96e4   # 75 nodes x 256 flop + ~0.4k contraction
 BYTES_PER_EVAL = 80.0    # read 5 + write 5 doubles
+REF_SAMPLE = 65536       # parcels per step of the CPU reference arm (bounded sample of the same generator)
 
 
 def parse():
@@ -38,29 +43,35 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--parcels", type=int, default=N_PARCELS, help="parcels per GPU")
+    ap.add_argument("--parcels", type=int, default=N_TOTAL, help="parcels of the whole job (sharded over the GPUs)")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--sums-every", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C2 1-Mi figure and the resident end-to-end leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
 
 def workload(n, seed_offset=0):
+    """the rank's shard: blocks of GEN_BLOCK parcels from the C2 generator (seeded per rank), repeated to n parcels"""
     from cloudy_b200 import workloads as W
-    return W.c2_gamma_exp(n_parcels=n, seed=W.SEED0 + 2 + seed_offset)
+    par, base = W.c2_gamma_exp(n_parcels=min(n, GEN_BLOCK), seed=W.SEED0 + 5 + seed_offset)
+    if n > base.shape[0]:
+        reps = (n + base.shape[0] - 1) // base.shape[0]
+        base = np.tile(base, (reps, 1))[:n]
+    return par, np.ascontiguousarray(base)
 
 
 def config_dict(args, world):
     return {
-        "workload": "C2 box model: Gamma cloud + Exponential rain, linear (Golovin) kernel, NProgMoms=(3,2) "
-                    "(5 moments, 6-slot reading of BASELINE.json), thresholds (0.5, Inf) normalised",
-        "parcels_per_gpu": args.parcels,
-        "global_parcels": args.parcels * world,
-        "parallelism": f"parcels block-partitioned over {world} GPU(s), no halo; NCCL all-reduce of 5 moment sums every "
-                       f"{args.sums_every} steps" if world > 1 else "single GPU",
-        "l2": "4 rotating input/output ensemble pairs (>= 336 MB at 1Mi parcels) so no step re-reads L2-resident data",
-        "step": "one rhs_coal! evaluation over every parcel of the rank",
+        "workload": "C5 = BASELINE.json configs[4]: C2 box-model ensemble (Gamma cloud + Exponential rain, linear (Golovin) kernel, "
+                    "NProgMoms=(3,2) = 5 moments, thresholds (0.5, Inf) normalised), 67,108,864 parcels sharded over the GPUs",
+        "global_parcels": args.parcels,
+        "parcels_per_gpu": args.parcels // max(world, 1),
+        "parallelism": f"parcels block-partitioned over {world} GPU(s) (strong scaling), no halo, no exchange; conservation all-reduce "
+                       f"of the 5 moment sums every {args.sums_every} steps through the C ABI (NCCL)",
+        "l2": "inputs exceed L2: 40 B x parcels per GPU read + the same written per step (2.7 GB at 1 GPU, 336 MB at 8 GPUs, L2 = 126 MB)",
+        "step": "one rhs_coal! evaluation over every parcel of the rank's shard",
     }
 
 
@@ -96,7 +107,7 @@ def run_reference(args):
         return
     from oracle import c_oracle
     threads = host_threads()
-    sample = 2048 * threads
+    sample = REF_SAMPLE
     par, state = workload(sample)
     import cloudy_b200 as cb
     cfg = cb.build_config(tuple(d.kind for d in par.pdists), par.coal_data, norms=par.norms)
@@ -107,14 +118,15 @@ def run_reference(args):
         c_oracle.rhs_coal_batch(cfg, state, n_threads=threads)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
+    desc = (f"each step = the first {sample} parcels of the same generator; C/OpenMP structure-faithful restatement of the Julia path "
+            f"(Julia is not installed; oracle/cloudy_oracle.c, {c_oracle.build_flags()}), {threads} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(config_dict(args, 1), step=f"one rhs_coal! evaluation over a bounded sample of {sample} parcels of the same workload"),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} parcels x {args.steps} steps; C/OpenMP structure-faithful restatement of the Julia path "
-                                   "(Julia is not installed; oracle/cloudy_oracle.c)"},
+        "config": config_dict(args, max(args.gpus, 1)),
+        "reference_sample": desc,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -181,10 +193,50 @@ def bind_to_gpu_numa_node(index):
         pass
 
 
+def profile_sidecar(parcels):
+    """newest committed ncu capture (profiles/*tpp_kernel_c5*.json, written by tools/ncu_summary.py --json) of this kernel on
+    a launch of `parcels` parcels: FP64-pipe utilisation, DRAM traffic and executed FP64 instructions are quoted from it
+    with the commit it was taken at — they are profiler counters, not measured in this run"""
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_tpp_kernel_c5*_ncu_full.json"))):
+        try:
+            d = json.load(open(path))
+            if int(d["meta"].get("parcels", 0)) == parcels:
+                best = (path, d)
+        except Exception:
+            continue
+    if best is None:
+        return None
+    path, d = best
+    m = d["metrics"]
+
+    def get(prefix):
+        for k, v in m.items():
+            if k.startswith(prefix):
+                return k, v
+        return None, None
+    out = {"file": os.path.relpath(path, ROOT), "git": d["meta"].get("git"), "parcels": parcels}
+    k, v = get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")
+    out["fp64_pipe_active"] = None if v is None else v / 100.0
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tr = 0.0
+    for pre in ("dram__bytes_read.sum [", "dram__bytes_write.sum ["):
+        k, v = get(pre)
+        if v is None:
+            tr = None
+            break
+        tr += v * scale.get(k.split("[")[1].rstrip("]"), 1.0)
+    out["traffic"] = tr
+    op = d.get("opcodes", {})
+    out["fp64_flop_per_parcel"] = (2.0 * op.get("DFMA", 0) + op.get("DMUL", 0) + op.get("DADD", 0)) * 32.0 / parcels
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
     import cloudy_b200 as cb
+    from cloudy_b200.parallel import init_comm, shard_range, total_mass
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,26 +255,17 @@ def run_b200(args):
     stream = tstream.cuda_stream
     assert stream != 0
     ctx = cb.Context(local, stream=stream)
-    n = args.parcels
+    init_comm(ctx, rank=rank, world=world)          # NCCL communicator inside the library (id shipped by torch.distributed)
+    lo, hi = shard_range(args.parcels, rank, world)
+    n = hi - lo
     par, state0 = workload(n, seed_offset=1000 * rank)
     model = cb.CoalescenceModel(par, ctx=ctx)
     if args.lanes:
         ctx.set_lanes(args.lanes)
-    NBUF = 4
-    ins, outs = [], []
-    for b in range(NBUF):
-        st = state0 if b == 0 else np.roll(state0, b * 977, axis=0)
-        ins.append(model.ensemble(n).upload(st))
-        outs.append(model.ensemble(n))
-    sums = torch.zeros(model.n_slots, dtype=torch.float64, device="cuda")
+    u = model.ensemble(n).upload(state0)
+    du = model.ensemble(n)
+    host_sums = state0.sum(axis=0)
     fp64_peak = ctx.measure_fp64_peak()
-
-    def step(i):
-        b = i % NBUF
-        model.coal_tendency(ins[b], outs[b])
-        if world > 1 and (i + 1) % args.sums_every == 0:
-            model.moment_sums_device(outs[b], sums.data_ptr())
-            dist.all_reduce(sums)
 
     def barrier():
         torch.cuda.synchronize()
@@ -230,15 +273,21 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    def step(i):
+        model.coal_tendency(u, du)                  # the first call moves the shard into regime order (once, untimed warm-up)
+        if (i + 1) % args.sums_every == 0:
+            model.moment_sums_allreduce(u, wait=False)   # side stream: overlaps the next step
+
+    warm = max(args.warmup, 3)
+    for i in range(warm):
         step(i)
+    sums = model.moment_sums_allreduce(u)           # checked below against the host sums of all shards
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
     l0 = ctx.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_start = torch.cuda.Event(enable_timing=True)
@@ -246,11 +295,10 @@ def run_b200(args):
     t_start.record()
     for i in range(args.steps):
         kev[i][0].record()
-        model.coal_tendency(ins[i % NBUF], outs[i % NBUF])
+        model.coal_tendency(u, du)
         kev[i][1].record()
-        if world > 1 and (i + 1) % args.sums_every == 0:
-            model.moment_sums_device(outs[i % NBUF], sums.data_ptr())
-            dist.all_reduce(sums)
+        if (i + 1) % args.sums_every == 0:
+            model.moment_sums_allreduce(u, wait=False)
     t_end.record()
     barrier()
     launches = ctx.launch_count() - l0
@@ -260,28 +308,38 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    # ---- sustained window: the same step repeated for ~1 s with the clock sampler running (the K timed steps above last
-    # only milliseconds, too short for nvidia-smi's sampling period); reported next to the burst value
-    sus_steps = int(min(5000, max(50, 1000.0 / max(total_ms / args.steps, 1e-3))))
+    try:
+        model.moment_sums_fetch()
+    except Exception:
+        pass
+    # conservation diagnostic: the all-reduced sums equal the sum of every rank's host shard
+    hs = torch.tensor(host_sums, dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(hs)
+    sums_ok = bool(np.allclose(sums, hs.cpu().numpy(), rtol=1e-11, atol=0.0))
+
+    # ---- sustained window: the same step repeated for ~1 s with the clock sampler running
+    sus_steps = int(min(5000, max(10, 1000.0 / max(total_ms / args.steps, 1e-3))))
     s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
     s0.record()
     for i in range(sus_steps):
-        model.coal_tendency(ins[i % NBUF], outs[i % NBUF])
+        model.coal_tendency(u, du)
     s1.record()
     barrier()
     ts_ = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
-    sustained_value = n * world * sus_steps / (float(ts_.item()) * 1e-3)
+    sustained_value = args.parcels * sus_steps / (float(ts_.item()) * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["window"] = f"timed region + {sus_steps} further identical steps ({float(ts_.item()):.0f} ms)"
+
     # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + kernel + D2H per step) ----
     h_in = torch.from_numpy(state0).pin_memory()
     h_out = torch.empty_like(h_in).pin_memory()
     hin_np, hout_np = h_in.numpy(), h_out.numpy()
-    e2e_steps = max(3, args.steps)
-    for _ in range(3):
+    e2e_steps = max(3, min(args.steps, 5))
+    for _ in range(2):
         model.coal_tendency_host(hin_np, hout_np)
     barrier()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -293,11 +351,52 @@ def run_b200(args):
     te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n * world * e2e_steps / (float(te.item()) * 1e-3)
+    e2e_value = args.parcels * e2e_steps / (float(te.item()) * 1e-3)
     checksum = float(np.abs(hout_np[:1024]).sum())
 
+    extras = {}
+    if not args.no_extras:
+        # ---- end to end with the state resident on the device: upload once, k fused SSPRK33 steps (3 RHS each), download once
+        k_res = 4
+        v = model.ensemble(n)
+        v.upload(hin_np); model.ssprk33_steps(v, 1e-3, 1, cb.MODEL_BOX); v.download(hout_np)   # warm-up (buffers, order)
+        barrier()
+        r0 = torch.cuda.Event(enable_timing=True); r1 = torch.cuda.Event(enable_timing=True)
+        r0.record()
+        v.upload(hin_np)
+        model.ssprk33_steps(v, 1e-3, k_res, cb.MODEL_BOX)
+        v.download(hout_np)
+        r1.record()
+        barrier()
+        tr = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        extras["e2e_resident"] = {"value": args.parcels * 3 * k_res / (float(tr.item()) * 1e-3), "unit": UNIT, "fused_steps": k_res,
+                                  "rhs_per_step": 3, "h2d_bytes": int(state0.nbytes), "d2h_bytes": int(state0.nbytes),
+                                  "api": "cloudy_state_upload -> cloudy_ssprk33_steps(k) -> cloudy_state_download (copies amortised over k steps)"}
+        v.close()
+        # ---- the C2 figure (BASELINE.json configs[1]): 1 Mi parcels per GPU, same kernel
+        n2 = 1 << 20
+        par2, st2 = workload(n2, seed_offset=1000 * rank + 7)
+        ins2 = [model.ensemble(n2).upload(np.roll(st2, b * 977, axis=0)) for b in range(4)]   # 4 x 84 MB > L2
+        outs2 = [model.ensemble(n2) for _ in range(4)]
+        for b in range(4):
+            model.coal_tendency(ins2[b], outs2[b])
+        barrier()
+        c0 = torch.cuda.Event(enable_timing=True); c1 = torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(20):
+            model.coal_tendency(ins2[i % 4], outs2[i % 4])
+        c1.record()
+        barrier()
+        tc = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        extras["c2_1mi_per_gpu"] = {"value": n2 * world * 20 / (float(tc.item()) * 1e-3), "unit": UNIT, "ms_per_step": float(tc.item()) / 20,
+                                    "note": "BASELINE.json configs[1]: 1,048,576 parcels per GPU, 4 rotating resident ensembles (> L2)"}
+
     if rank == 0:
-        value = n * world * args.steps / (total_ms * 1e-3)
+        value = args.parcels * args.steps / (total_ms * 1e-3)
         k_ms = float(np.mean(kernel_ms))
         peaks = {}
         try:
@@ -306,43 +405,56 @@ def run_b200(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         achieved_tf = FLOP_PER_EVAL * n / (k_ms * 1e-3) / 1e12
+        prof = profile_sidecar(n)
+        sm_mhz = (clocks or {}).get("sm_mhz")
+        nominal_at_clock = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12 if sm_mhz else None
+        roof = {
+            "bound": "fp64", "kernel": "tpp_kernel<2,2,BOX>", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": achieved_tf / fp64_peak if fp64_peak else None,
+            "peak_source": "DFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+            "peak_nominal_at_sampled_clock": nominal_at_clock,
+            "flop_per_eval": FLOP_PER_EVAL, "kernel_ms": k_ms,
+            "note": "achieved = nominal algorithmic flop model of SURVEY 8(d) (two exp + one incomplete gamma per node, integral entries "
+                    "sharing nothing) x parcels / event-timed kernel duration; the kernel EXECUTES fewer FP64 instructions than that model "
+                    "(one exp per node, shared incomplete gamma), see executed_fp64_tflops",
+            "hbm": {"achieved": BYTES_PER_EVAL * n / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": BYTES_PER_EVAL * n / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+            "algorithmic_bytes": BYTES_PER_EVAL * n,
+            "traffic": None, "fp64_pipe_active_ncu": None, "executed_fp64_tflops": None, "profile": None,
+        }
+        if prof is not None:
+            roof["traffic"] = prof["traffic"]
+            roof["fp64_pipe_active_ncu"] = prof["fp64_pipe_active"]
+            roof["executed_fp64_tflops"] = prof["fp64_flop_per_parcel"] * n / (k_ms * 1e-3) / 1e12
+            roof["executed_fp64_frac"] = roof["executed_fp64_tflops"] / fp64_peak if fp64_peak else None
+            roof["profile"] = {"file": prof["file"], "git": prof["git"], "parcels_per_launch": prof["parcels"],
+                               "note": "ncu --set full capture of the same kernel and launch size; traffic, FP64-pipe utilisation and the executed "
+                                       "DFMA/DMUL/DADD counts come from it, the duration does not"}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config_dict(args, world),
             "pair_evals_per_s": value * 4,  # parcel-mode-pair evals/s = value x N^2
             "sustained": {"value": sustained_value, "unit": UNIT, "steps": sus_steps},
-            "roofline": {
-                "bound": "fp64", "kernel": "tpp_kernel<2,2,BOX>", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": achieved_tf / fp64_peak if fp64_peak else None,
-                "peak_source": "DFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry); nominal 37.2",
-                "flop_per_eval": FLOP_PER_EVAL, "kernel_ms": k_ms,
-                # sm__pipe_fp64_cycles_active of the same kernel and workload, ncu --set full (not measured in this run):
-                "fp64_pipe_active_ncu": 0.535 if n == (1 << 20) else None,
-                "note": "achieved = nominal algorithmic flop model of SURVEY 8(d) (two exp + one incomplete gamma per node and integral "
-                        "entry sharing none) x parcels / time; the kernel EXECUTES ~4x fewer FP64 instructions than that model (one exp per "
-                        "node, Taylor evaluation of the shared incomplete gamma), so frac ~ 1 coexists with ~50% FP64-pipe utilisation "
-                        "(profiles/r01_tpp_kernel_c2_ncu_full_summary.txt); kernel_ms includes the 2 regime-sort launches of each step",
-                "hbm": {"achieved": BYTES_PER_EVAL * n / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": BYTES_PER_EVAL * n / (k_ms * 1e-3) / 1e9 / hbm_peak,
-                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-                # dram__bytes_read.sum + dram__bytes_write.sum of one tpp_kernel launch over 1 Mi parcels, ncu --set full
-                # (profiles/r01_tpp_kernel_c2_ncu_full_summary.txt): 84.5 + 39.1 MB vs 84 MB algorithmic (the regime-sorted gather
-                # touches 32-byte sectors for 8-byte loads); irrelevant to the FP64-bound duration
-                "traffic": 123.6e6 if n == (1 << 20) else None,
-            },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(state0.nbytes), "d2h_bytes_per_step": int(state0.nbytes),
-                    "steps": e2e_steps, "api": "cloudy_coal_tendency_host (pinned host buffers)", "checksum": checksum},
+            "roofline": roof,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(state0.nbytes) * world, "d2h_bytes_per_step": int(state0.nbytes) * world,
+                    "steps": e2e_steps, "api": "cloudy_coal_tendency_host (pinned host buffers, H2D + kernel + D2H inside the timed region)",
+                    "checksum": checksum},
+            "conservation": {"allreduce": "cloudy_moment_sums_allreduce (C ABI, NCCL)", "sums_match_host": sums_ok,
+                             "total_mass": total_mass(sums, par.NProgMoms)},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        line.update(extras)
         if not args.no_cpu_baseline and world == 1:
             os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core again
             threads = host_threads()
+            from oracle import c_oracle
             rate, ns, dt = cpu_rate(par, state0, args.cpu_seconds, threads)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"first {ns} parcels of the same ensemble, {dt:.1f} s; C/OpenMP structure-faithful "
-                                              "restatement of the Julia path (oracle/cloudy_oracle.c)"}
+                                    "sample": f"first {ns} parcels of the same shard, {dt:.1f} s; C/OpenMP structure-faithful "
+                                              f"restatement of the Julia path (oracle/cloudy_oracle.c, {c_oracle.build_flags()})"}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -1,6 +1,15 @@
 """Summarise an ncu report: key raw metrics + top CUDA source lines + opcode mix (development aid)."""
-import csv, subprocess, sys, re, collections, io
+import csv, subprocess, sys, re, collections, io, json, os
 rep = sys.argv[1]
+# optional: --json <file> [--meta key=value ...]: machine-readable sidecar bench.py reads (profiles/*.json)
+json_out = None; meta = {}
+if "--json" in sys.argv:
+    i = sys.argv.index("--json"); json_out = sys.argv[i + 1]
+    for kv in sys.argv[i + 2:]:
+        if "=" in kv:
+            k_, v_ = kv.split("=", 1); meta[k_] = v_
+    del sys.argv[i:]
+side = {"report": os.path.basename(rep), "meta": meta, "metrics": {}, "opcodes": {}}
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
@@ -13,6 +22,8 @@ for r in rows[2:]:
     print("==", r[hdr.index('Kernel Name')][:90] if 'Kernel Name' in hdr else '')
     for h, u, v in zip(hdr, units, r):
         if any(h.startswith(k.strip()) if k.endswith(' ') else (k in h) for k in keys):
+            try: side["metrics"][h + " [" + u + "]"] = float(v.replace(",", ""))
+            except Exception: pass
             if 'stalled' in h and float(v or 0) < 0.15: continue
             print(f"  {h} [{u}] = {v}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
@@ -33,5 +44,9 @@ tot = sum(a[3] for a in agg) or 1; tots = sum(a[4] for a in agg) or 1
 print("-- top source lines (instr %, stall-sample %)")
 for a in sorted(agg, key=lambda a: -a[3])[:int(sys.argv[2]) if len(sys.argv) > 2 else 30]:
     print(f"{a[3]/tot*100:5.1f}% {a[4]/tots*100:5.1f}%  {a[0]}:{a[1]}: {a[2]}")
+side["opcodes"] = {o: n for o, n in op.most_common(40)}   # warp-level executed instruction counts by opcode
+side["warp_instructions"] = tot_sass
+if json_out:
+    with open(json_out, "w") as f: json.dump(side, f, indent=1)
 print("-- opcode mix")
 print("  ".join(f"{o}:{n/tot_sass*100:.1f}%" for o, n in op.most_common(16)))
