@@ -679,6 +679,29 @@ __global__ void scalar_kernel(const ScalarArgs a) {
             const double x = (a.kind == CLOUDY_GAMMA) ? th * igam_inv(a.params[2], a.q) : -th * log(1.0 - a.q);
             a.out[0] = fmax(x, a.p1);
         }
+    } else if (a.op == 6) {
+        // moment_source_helper for a Lognormal mode with real p1, p2 (ParticleDistributions.jl:614-625): inner integral in closed
+        // form, outer integral by the same fixed Gauss-Legendre rule in t = ln y as the batched path (tpp_lognormal_H);
+        // a.y = rule nodes then weights, a.n_bins = rule size
+        const double n = a.params[0], mu = a.params[1], sg = a.params[2], s2 = sg * sg;
+        const double hi = fmin(log(a.x_th), mu + fmax(fmax(a.p1, a.p2), 0.0) * s2 + 12.0 * sg);
+        const double lo = mu - 12.0 * sg;
+        double part = 0.0;
+        if (hi > lo) {
+            const double half = 0.5 * (hi - lo), mid = 0.5 * (hi + lo), inv_sg = 1.0 / sg;
+            const double pref = n * inv_sg * 0.3989422804014327;  // n / (σ sqrt(2π))
+            const double c1 = n * exp(a.p1 * mu + a.p1 * a.p1 * s2 / 2);
+            for (int q = lane; q < a.n_bins; q += 32) {
+                const double t = fma(half, a.y[q], mid);
+                const double y = exp(t);
+                const double dd = (t - mu) * inv_sg;
+                const double rem = a.x_th - y;
+                const double inner = (rem > 0.0) ? c1 * norm_cdf((log(fmax(rem, 1e-300)) - mu - a.p1 * s2) * inv_sg) : 0.0;
+                part += a.y[a.n_bins + q] * half * pref * exp(fma(a.p2, t, -0.5 * dd * dd)) * inner;  // weight * y^p2 f(y) y * inner
+            }
+        }
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+        if (lane == 0) a.out[0] = part;
     } else if (a.op == 4) {
         double part = 0.0;
         for (int j = 1 + lane; j <= a.n_bins + 1; j += 32) part += simpson_weight(j, a.n_bins) * a.y[j - 1];
@@ -698,9 +721,11 @@ __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevCo
 #pragma unroll
             for (int q = 0; q < 3; ++q)
                 raw[i][q] = (i < cfg.N && q < cfg.nprog[i]) ? __ldg(args.u_in + (cfg.slot0[i] + q) * args.s_in + p * args.ps_in) : 0.0;
+        double pn[MAXN], pa[MAXN], pb[MAXN];
 #pragma unroll
         for (int i = 0; i < MAXN; ++i) {
-            if (i >= cfg.N) break;
+            pn[i] = 0.0; pa[i] = 1.0; pb[i] = 1.0;
+            if (i >= cfg.N) continue;
             const int s0 = cfg.slot0[i], np = cfg.nprog[i], kind = cfg.kind[i];
             double mn[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -712,26 +737,16 @@ __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevCo
             }
             const ModeParams mp = params_from_moments(kind, mn[0], mn[1], mn[2], kind == CLOUDY_GAMMA ? cfg.k_lo : -INFINITY,
                                                       kind == CLOUDY_GAMMA ? cfg.k_hi : INFINITY);
-            double fl[3] = {0.0, 0.0, 0.0};
-            if (mp.n != 0.0) {  // an empty mode (n = 0, the fallback of update_dist_from_moments) carries no flux
-                const double log_a = (kind == CLOUDY_LOGNORMAL) ? 0.0 : log(mp.a);
-                for (int v = 0; v < cfg.n_vel; ++v) {
-                    const double beta = cfg.velb[v];
-                    // moment(dist, beta): n θ^β Γ(β+k)/Γ(k) | n θ^β Γ(β+1) | n θ^β  (ParticleDistributions.jl:177-199)
-                    double mq = 0.0;
-                    if (kind == CLOUDY_GAMMA) mq = mp.n * exp(beta * log_a) * gamma_ratio(mp.b, beta);
-                    else if (kind == CLOUDY_EXPONENTIAL) mq = mp.n * exp(beta * log_a) * cfg.gam_b1[v];
-                    else if (kind == CLOUDY_MONODISPERSE) mq = mp.n * exp(beta * log_a);
-                    for (int q = 0; q < np; ++q) {
-                        if (kind == CLOUDY_LOGNORMAL) mq = moment_real(kind, mp.n, mp.a, mp.b, (double)q + beta);
-                        fl[q] += -cfg.velv[v] * mq;
-                        if (kind == CLOUDY_GAMMA) mq *= mp.a * (mp.b + beta + q);
-                        else if (kind == CLOUDY_EXPONENTIAL) mq *= mp.a * (beta + q + 1.0);
-                        else mq *= mp.a;
-                    }
-                }
-            }
-            for (int q = 0; q < np; ++q) args.out[(s0 + q) * args.s_out + p * args.ps_out] = fl[q] * cfg.norm[s0 + q];
+            pn[i] = mp.n; pa[i] = mp.a; pb[i] = mp.b;
+        }
+        double fl[MAXN][3];
+        cell_flux<MAXN>(cfg, pn, pa, pb, fl);
+#pragma unroll
+        for (int i = 0; i < MAXN; ++i) {
+            if (i >= cfg.N) continue;
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (q < cfg.nprog[i]) args.out[(cfg.slot0[i] + q) * args.s_out + p * args.ps_out] = fl[i][q];
         }
     }
 }
@@ -1017,6 +1032,28 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, 
 // host side: C ABI
 // ================================================================================================
 using namespace cloudy;
+
+// Gauss-Legendre rule on [-1, 1] (Newton iteration on the Legendre polynomial): nodes xs[n], weights ws[n]
+static void gauss_legendre_rule(int n, double* xs, double* ws) {
+    for (int i = 0; i < (n + 1) / 2; ++i) {
+        double x = cos(M_PI * (i + 0.75) / (n + 0.5)), pp = 0.0;
+        for (int it = 0; it < 100; ++it) {
+            double p1 = 1.0, p2 = 0.0;
+            for (int j = 0; j < n; ++j) {
+                const double p3 = p2;
+                p2 = p1;
+                p1 = ((2.0 * j + 1.0) * x * p2 - j * p3) / (j + 1.0);
+            }
+            pp = n * (x * p1 - p2) / (x * x - 1.0);
+            const double dxn = p1 / pp;
+            x -= dxn;
+            if (fabs(dxn) < 1e-16) break;
+        }
+        xs[i] = -x; xs[n - 1 - i] = x;
+        ws[i] = ws[n - 1 - i] = 2.0 / ((1.0 - x * x) * pp * pp);
+    }
+}
+constexpr int kLognormalGL = 128;  // points of the Lognormal moment_source_helper rule (batched and scalar paths)
 
 static thread_local std::string g_last_error;
 static int fail(int code, const std::string& msg) {
@@ -1718,28 +1755,12 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
         }
     }
     if (any_ln) {
-        // Gauss-Legendre rule on [-1, 1] (Newton iteration on the Legendre polynomial), nodes then weights
-        const int n = 128;
+        // Gauss-Legendre rule on [-1, 1], nodes then weights
+        const int n = kLognormalGL;
         d.gl_off = (int)tab2.size();
         d.gl_n = n;
         std::vector<double> xs(n), ws(n);
-        for (int i = 0; i < (n + 1) / 2; ++i) {
-            double x = cos(M_PI * (i + 0.75) / (n + 0.5)), pp = 0.0;
-            for (int it = 0; it < 100; ++it) {
-                double p1 = 1.0, p2 = 0.0;
-                for (int j = 0; j < n; ++j) {
-                    const double p3 = p2;
-                    p2 = p1;
-                    p1 = ((2.0 * j + 1.0) * x * p2 - j * p3) / (j + 1.0);
-                }
-                pp = n * (x * p1 - p2) / (x * x - 1.0);
-                const double dxn = p1 / pp;
-                x -= dxn;
-                if (fabs(dxn) < 1e-16) break;
-            }
-            xs[i] = -x; xs[n - 1 - i] = x;
-            ws[i] = ws[n - 1 - i] = 2.0 / ((1.0 - x * x) * pp * pp);
-        }
+        gauss_legendre_rule(n, xs.data(), ws.data());
         tab2.insert(tab2.end(), xs.begin(), xs.end());
         tab2.insert(tab2.end(), ws.begin(), ws.end());
     }
@@ -1785,6 +1806,38 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
     }
     d.nz = cfg->nz > 0 ? cfg->nz : 1;
     d.dz = cfg->dz;
+    // Γ(k+β+1)/Γ(k+1) per velocity term: degree-7 Chebyshev interpolants on kGrIntervals intervals of [0, k_max], stored as
+    // monomial coefficients in t in [-1, 1] (special.cuh gamma_ratio_tab)
+    {
+        const double k_max = std::max(d.k_hi, 1.0) + 0.01;
+        const double h = k_max / kGrIntervals;
+        d.gr_inv_h = 1.0 / h;
+        // T_n(t) as monomials
+        double T[kGrCoef][kGrCoef] = {{0}};
+        T[0][0] = 1.0; T[1][1] = 1.0;
+        for (int n = 2; n < kGrCoef; ++n)
+            for (int m = 0; m < kGrCoef; ++m) T[n][m] = (m > 0 ? 2.0 * T[n - 1][m - 1] : 0.0) - T[n - 2][m];
+        for (int v = 0; v < d.n_vel; ++v) {
+            d.gr_off[v] = (int)tab.size();
+            const double beta = d.velb[v];
+            for (int i = 0; i < kGrIntervals; ++i) {
+                double f[kGrCoef], tn[kGrCoef];
+                for (int j = 0; j < kGrCoef; ++j) {
+                    tn[j] = cos(M_PI * (j + 0.5) / kGrCoef);
+                    const double k = (i + 0.5 * (tn[j] + 1.0)) * h;
+                    f[j] = exp(lgamma(k + beta + 1.0) - lgamma(k + 1.0));
+                }
+                double mono[kGrCoef] = {0};
+                for (int n = 0; n < kGrCoef; ++n) {
+                    double cn = 0.0;
+                    for (int j = 0; j < kGrCoef; ++j) cn += f[j] * cos(M_PI * n * (j + 0.5) / kGrCoef);
+                    cn *= (n == 0 ? 1.0 : 2.0) / kGrCoef;
+                    for (int m = 0; m < kGrCoef; ++m) mono[m] += cn * T[n][m];
+                }
+                for (int m = 0; m < kGrCoef; ++m) tab.push_back(mono[m]);
+            }
+        }
+    }
     double* new_tab = nullptr;
     if (!tab.empty()) {
         CUDA_TRY(cudaMalloc(&new_tab, sizeof(double) * tab.size()));
@@ -2370,7 +2423,19 @@ int cloudy_moment_source_helper(cloudy_ctx* ctx, int32_t kind, const double* par
         *out = (params[1] < x_threshold / 2) ? v : 0.0;
         return CLOUDY_OK;
     }
-    if (kind == CLOUDY_LOGNORMAL) return fail(CLOUDY_ERR_UNSUPPORTED, "moment_source_helper(Lognormal): use a configured model (batched path only)");
+    if (kind == CLOUDY_LOGNORMAL) {
+        if (!(x_threshold > 0)) return fail(CLOUDY_ERR_ARG, "x_threshold must be positive");
+        if (!(params[2] > 0)) return fail(CLOUDY_ERR_ARG, "sigma needs to be positive");
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        double rule[2 * kLognormalGL];
+        gauss_legendre_rule(kLognormalGL, rule, rule + kLognormalGL);
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_scratch + 64, rule, sizeof(rule), cudaMemcpyHostToDevice, ctx->stream));
+        ScalarArgs a;
+        memset(&a, 0, sizeof(a));
+        a.op = 6; a.kind = kind; a.p1 = p1; a.p2 = p2; a.x_th = x_threshold; a.n_bins = kLognormalGL; a.y = ctx->d_scratch + 64;
+        for (int i = 0; i < 3; ++i) a.params[i] = params[i];
+        return run_scalar(ctx, a, out, 1, nullptr);  // (synchronises: `rule` stays alive until the copy has landed)
+    }
     if (kind != CLOUDY_EXPONENTIAL && kind != CLOUDY_GAMMA) return fail(CLOUDY_ERR_ARG, "unknown distribution kind");
     if (!(x_threshold > 0)) return fail(CLOUDY_ERR_ARG, "x_threshold must be positive");
     ScalarArgs a;

@@ -47,6 +47,8 @@ struct DevConfig {
     double xp_k0, xp_inv_h;
     double velv[CLOUDY_MAX_VEL], velb[CLOUDY_MAX_VEL];  // v*norms[2]^beta, beta
     double gam_b1[CLOUDY_MAX_VEL];                      // Γ(1 + beta): Exponential modes' fractional moment
+    int gr_off[CLOUDY_MAX_VEL];                         // per velocity term: Γ(k+β+1)/Γ(k+1) polynomial table inside `tab` (special.cuh gamma_ratio_tab)
+    double gr_inv_h;                                    // intervals per unit of k
     double inv_dz_unused, dz;
     const double* tab;  // device: per quad mode i at tab_off[i]: XJ[n] ELL[n] TMX[n] LZ[n] W[M][n]
 };
@@ -126,6 +128,46 @@ __device__ inline double moment_real(int kind, double n, double a, double b, dou
         case CLOUDY_GAMMA: return n * pow(a, q) * tgamma(q + b) / tgamma(b);
         case CLOUDY_MONODISPERSE: return n * pow(a, q);
         default: return n * exp(q * a + q * q * b * b / 2);
+    }
+}
+
+// Sedimentation flux of one cell from its distribution parameters — Sedimentation.jl:22-37 with the velocity normalisation of
+// rainshaft_helpers.jl:74-77: flux[i][q] = s_q * (-sum_l v_l x0^beta_l moment(pdist_i, q + beta_l)).  moment(dist, q+β) for
+// q = 0,1,2 follows from the q = 0 value by Γ(x+1) = xΓ(x).  An empty mode (n = 0, the fallback of update_dist_from_moments)
+// carries no flux.  Used by flux_kernel (cloudy_sedimentation_flux) and, for a cell and the cell above it, inside the
+// rainshaft instances of the thread-per-parcel kernel.
+template <int NM>
+__device__ __forceinline__ void cell_flux(const DevConfig& cfg, const double (&pn)[NM], const double (&pa)[NM], const double (&pb)[NM],
+                                          double (&fl)[NM][3]) {
+#pragma unroll
+    for (int i = 0; i < NM; ++i) {
+        fl[i][0] = fl[i][1] = fl[i][2] = 0.0;
+        if (i >= cfg.N) continue;
+        const int np = cfg.nprog[i], kind = cfg.kind[i];
+        if (pn[i] != 0.0) {
+            const double log_a = (kind == CLOUDY_LOGNORMAL) ? 0.0 : log(pa[i]);
+            for (int v = 0; v < cfg.n_vel; ++v) {
+                const double beta = cfg.velb[v];
+                // moment(dist, beta): n θ^β Γ(β+k)/Γ(k) | n θ^β Γ(β+1) | n θ^β  (ParticleDistributions.jl:177-199)
+                double mq = 0.0;
+                if (kind == CLOUDY_GAMMA) mq = pn[i] * exp(beta * log_a) * gamma_ratio_tab(pb[i], beta, cfg.tab + cfg.gr_off[v], cfg.gr_inv_h);
+                else if (kind == CLOUDY_EXPONENTIAL) mq = pn[i] * exp(beta * log_a) * cfg.gam_b1[v];
+                else if (kind == CLOUDY_MONODISPERSE) mq = pn[i] * exp(beta * log_a);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if (q < np) {
+                        if (kind == CLOUDY_LOGNORMAL) mq = moment_real(kind, pn[i], pa[i], pb[i], (double)q + beta);
+                        fl[i][q] += -cfg.velv[v] * mq;
+                        if (kind == CLOUDY_GAMMA) mq *= pa[i] * (pb[i] + beta + q);
+                        else if (kind == CLOUDY_EXPONENTIAL) mq *= pa[i] * (beta + q + 1.0);
+                        else mq *= pa[i];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (q < np) fl[i][q] *= cfg.norm[cfg.slot0[i] + q];
     }
 }
 

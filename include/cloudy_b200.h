@@ -197,7 +197,10 @@ int cloudy_moment(cloudy_ctx* ctx, int32_t kind, const double* params, double q,
  * *invalid = 1 where the reference would throw a DomainError. */
 int cloudy_update_dist_from_moments(cloudy_ctx* ctx, int32_t kind, const double* moments, const double* range,
                                     double* params_out, int32_t* invalid);
-/* moment_source_helper(dist, p1, p2, x_threshold, n_bins_per_log_unit) — ParticleDistributions.jl:557-625 */
+/* moment_source_helper(dist, p1, p2, x_threshold, n_bins_per_log_unit) — ParticleDistributions.jl:557-625, every distribution
+ * kind.  Exponential / Gamma: the reference's log-spaced Simpson rule on the reference's nodes (:567-612); Monodisperse: closed
+ * form (:557-564); Lognormal (:614-625, two nested adaptive QuadGK calls at rtol sqrt(eps) in the reference): inner integral
+ * in closed form, outer integral by a fixed 128-point Gauss-Legendre rule in ln y (n_bins_per_log_unit is ignored). */
 int cloudy_moment_source_helper(cloudy_ctx* ctx, int32_t kind, const double* params, double p1, double p2,
                                 double x_threshold, int32_t n_bins_per_log_unit, double* out);
 /* compute_threshold(pdist, percentile, minx) — ParticleDistributions.jl:747-761 (Exponential: -θ log(1-p); Gamma: θ gamma_inc_inv(k, p)) */

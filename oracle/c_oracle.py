@@ -43,6 +43,13 @@ def load():
         _lib.cloudy_oracle_rhs_coal_batch.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64, C.c_int]
         _lib.cloudy_oracle_rhs_coal_batch.restype = C.c_int
         _lib.cloudy_oracle_max_threads.restype = C.c_int
+        D = C.POINTER(C.c_double)
+        _lib.cloudy_oracle_sedimentation_flux_batch.argtypes = [C.c_void_p, D, D, C.c_int64]
+        _lib.cloudy_oracle_sedimentation_flux_batch.restype = C.c_int
+        _lib.cloudy_oracle_rainshaft_rhs.argtypes = [C.c_void_p, D, D, C.c_int64, C.c_int]
+        _lib.cloudy_oracle_rainshaft_rhs.restype = C.c_int
+        _lib.cloudy_oracle_ssprk33.argtypes = [C.c_void_p, D, C.c_double, C.c_int, C.c_int, C.c_int64, C.c_int]
+        _lib.cloudy_oracle_ssprk33.restype = C.c_int
         _lib.cloudy_oracle_moment_source_helper.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double,
                                                             C.c_int, C.c_double, C.c_double]
         _lib.cloudy_oracle_moment_source_helper.restype = C.c_double
@@ -66,3 +73,37 @@ def rhs_coal_batch(cfg_struct, states, n_threads=0):
     if rc != 0:
         raise RuntimeError(f"oracle returned {rc}")
     return out
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def sedimentation_flux_batch(cfg_struct, states):
+    """get_sedimentation_flux .* mom_norms of every cell (Sedimentation.jl:22-37, rainshaft_helpers.jl:74-77); states (n, n_slots)."""
+    a = np.ascontiguousarray(states, dtype=np.float64)
+    out = np.empty_like(a)
+    rc = load().cloudy_oracle_sedimentation_flux_batch(C.byref(cfg_struct), _dp(a), _dp(out), a.shape[0])
+    if rc != 0:
+        raise RuntimeError(f"oracle returned {rc}")
+    return out
+
+
+def rainshaft_rhs(cfg_struct, columns, n_threads=0):
+    """rainshaft_helpers.jl:47-88 for columns (n_columns, nz, n_slots); ``columns`` is clipped IN PLACE like the reference."""
+    if not (columns.flags.c_contiguous and columns.dtype == np.float64):
+        raise ValueError("columns must be a C-contiguous float64 array (it is clipped in place)")
+    out = np.empty_like(columns)
+    rc = load().cloudy_oracle_rainshaft_rhs(C.byref(cfg_struct), _dp(columns), _dp(out), columns.shape[0], int(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle returned {rc}")
+    return out
+
+
+def ssprk33(cfg_struct, u0, dt, n_steps, model=0, n_threads=0):
+    """n_steps of SSPRK33 on a copy of u0: model 0 = box (u0 (n, n_slots)), model 1 = rainshaft (u0 (n_columns, nz, n_slots))."""
+    u = np.array(u0, dtype=np.float64, order="C", copy=True)
+    rc = load().cloudy_oracle_ssprk33(C.byref(cfg_struct), _dp(u), float(dt), int(n_steps), int(model), u.shape[0], int(n_threads))
+    if rc != 0:
+        raise RuntimeError(f"oracle returned {rc}")
+    return u

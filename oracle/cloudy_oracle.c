@@ -17,11 +17,15 @@
  *   src/helper_functions.jl:40-53                       normalising factors
  *   src/ParticleDistributions/ParticleDistributions.jl:177-207, :456-541, :557-612, :698-710
  *   src/Sources/Coalescence.jl:115-150, :187-455
+ *   src/Sources/Sedimentation.jl:22-37                  get_sedimentation_flux
+ *   test/examples/utils/rainshaft_helpers.jl:47-88      make_rainshaft_rhs body
+ *   OrdinaryDiffEqSSPRK SSPRK33 (third-party): Shu-Osher SSP(3,3), fixed dt
  * gamma / gamma_inc come from SpecialFunctions.jl (compat "2.5", not vendored); here: libm tgamma and the
  * published series / continued-fraction expansions of P(a,x).
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -223,6 +227,123 @@ int cloudy_oracle_rhs_coal_batch(const cloudy_config* cfg, const double* m, doub
         }
         for (int s = 0; s < nslots; ++s) dm[p * nslots + s] = ci[s] * norm[s];
     }
+    return status;
+}
+
+/* ---- layout helpers ---- */
+static int slot_layout(const cloudy_config* cfg, int* slot0, double* norm) {
+    int nslots = 0;
+    for (int i = 0; i < cfg->n_modes; ++i) {
+        slot0[i] = nslots;
+        for (int q = 0; q < cfg->nprog[i]; ++q) norm[nslots++] = cfg->norms[0] * pow(cfg->norms[1], (double)q);
+    }
+    return nslots;
+}
+
+/* get_sedimentation_flux(pdists, vel) .* mom_norms with vel normalised as rainshaft_helpers.jl:74-77 — Sedimentation.jl:22-37 */
+static void sedimentation_flux_cell(const cloudy_config* cfg, const dist_t* pd, const int* slot0, const double* norm, double* out) {
+    for (int i = 0; i < cfg->n_modes; ++i)
+        for (int j = 0; j < cfg->nprog[i]; ++j) {
+            double sacc = 0.0;
+            for (int v = 0; v < cfg->n_vel; ++v) {
+                const double beta = cfg->vel[v][1];
+                const double vn = cfg->vel[v][0] * pow(cfg->norms[1], beta);
+                sacc += -vn * moment(&pd[i], (double)j + beta);
+            }
+            out[slot0[i] + j] = sacc * norm[slot0[i] + j];
+        }
+}
+
+/* sedimentation flux of n cells, AoS [n][n_slots] (no clipping: the caller passes the state it wants evaluated) */
+int cloudy_oracle_sedimentation_flux_batch(const cloudy_config* cfg, const double* m, double* out, int64_t n) {
+    int slot0[CLOUDY_MAX_MODES];
+    double norm[CLOUDY_MAX_SLOTS];
+    const int nslots = slot_layout(cfg, slot0, norm);
+    for (int64_t p = 0; p < n; ++p) {
+        dist_t pd[CLOUDY_MAX_MODES];
+        double mn[CLOUDY_MAX_SLOTS];
+        for (int s = 0; s < nslots; ++s) mn[s] = m[p * nslots + s] / norm[s];
+        for (int i = 0; i < cfg->n_modes; ++i) pd[i] = update_dist_from_moments(cfg->kind[i], mn + slot0[i], cfg->k_range);
+        sedimentation_flux_cell(cfg, pd, slot0, norm, out + p * nslots);
+    }
+    return 0;
+}
+
+/* the column right-hand side — rainshaft_helpers.jl:47-88.  `m` is [n_columns][nz][n_slots] and is CLIPPED IN PLACE (:52);
+ * per level: coalescence (zero when every normalised moment is below eps, :67-68) + sedimentation flux; zero flux above
+ * the top (:80-81); first-order upwind divergence (:83-85). */
+int cloudy_oracle_rainshaft_rhs(const cloudy_config* cfg, double* m, double* dm, int64_t n_columns, int n_threads) {
+    int slot0[CLOUDY_MAX_MODES];
+    double norm[CLOUDY_MAX_SLOTS];
+    const int nslots = slot_layout(cfg, slot0, norm);
+    const int nz = cfg->nz;
+    const int64_t n = n_columns * nz;
+    int status = 0;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+    for (int64_t q = 0; q < n * nslots; ++q)
+        if (m[q] < 0.0) m[q] = 0.0;
+    /* dm first receives the coalescence source; the flux of every cell goes to a scratch array of the same shape */
+    double* flux = (double*)malloc(sizeof(double) * (size_t)n * nslots);
+    if (!flux) return CLOUDY_ERR_ARG;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t p = 0; p < n; ++p) {
+        dist_t pd[CLOUDY_MAX_MODES];
+        double mn[CLOUDY_MAX_SLOTS], ci[CLOUDY_MAX_SLOTS];
+        int all_small = 1;
+        for (int s = 0; s < nslots; ++s) {
+            mn[s] = m[p * nslots + s] / norm[s];
+            if (!(mn[s] < EPS)) all_small = 0;
+        }
+        for (int i = 0; i < cfg->n_modes; ++i) pd[i] = update_dist_from_moments(cfg->kind[i], mn + slot0[i], cfg->k_range);
+        if (all_small) {
+            for (int s = 0; s < nslots; ++s) dm[p * nslots + s] = 0.0;
+        } else {
+            int rc = get_coal_ints(cfg, pd, ci);
+            if (rc) {
+#pragma omp atomic write
+                status = rc;
+            }
+            for (int s = 0; s < nslots; ++s) dm[p * nslots + s] = ci[s] * norm[s];
+        }
+        sedimentation_flux_cell(cfg, pd, slot0, norm, flux + p * nslots);
+    }
+    for (int64_t c = 0; c < n_columns; ++c)
+        for (int z = 0; z < nz; ++z) {
+            const int64_t p = c * nz + z;
+            for (int s = 0; s < nslots; ++s) {
+                const double up = (z == nz - 1) ? 0.0 : flux[(p + 1) * nslots + s];
+                dm[p * nslots + s] = dm[p * nslots + s] + (-(up - flux[p * nslots + s]) / cfg->dz);
+            }
+        }
+    free(flux);
+    return status;
+}
+
+/* n_steps of SSPRK33 (u1 = u + dt f(u); u2 = (3u + u1 + dt f(u1))/4; u+ = (u + 2 u2 + 2 dt f(u2))/3), in place.
+ * model 0: box (rhs_coal! per parcel, `n` parcels); model 1: rainshaft (`n` columns of cfg->nz cells; the right-hand side
+ * clips the array it is evaluated at, as the reference does). */
+int cloudy_oracle_ssprk33(const cloudy_config* cfg, double* u, double dt, int n_steps, int model, int64_t n, int n_threads) {
+    int slot0[CLOUDY_MAX_MODES];
+    double norm[CLOUDY_MAX_SLOTS];
+    const int nslots = slot_layout(cfg, slot0, norm);
+    const int64_t cells = (model == 1) ? n * cfg->nz : n;
+    const size_t len = (size_t)cells * nslots;
+    double* k = (double*)malloc(sizeof(double) * len);
+    double* tmp = (double*)malloc(sizeof(double) * len);
+    if (!k || !tmp) { free(k); free(tmp); return CLOUDY_ERR_ARG; }
+    int status = 0;
+    for (int step = 0; step < n_steps && !status; ++step) {
+        status = (model == 1) ? cloudy_oracle_rainshaft_rhs(cfg, u, k, n, n_threads) : cloudy_oracle_rhs_coal_batch(cfg, u, k, n, n_threads);
+        for (size_t i = 0; i < len; ++i) tmp[i] = u[i] + dt * k[i];
+        if (!status) status = (model == 1) ? cloudy_oracle_rainshaft_rhs(cfg, tmp, k, n, n_threads) : cloudy_oracle_rhs_coal_batch(cfg, tmp, k, n, n_threads);
+        for (size_t i = 0; i < len; ++i) tmp[i] = (3 * u[i] + tmp[i] + dt * k[i]) / 4;
+        if (!status) status = (model == 1) ? cloudy_oracle_rainshaft_rhs(cfg, tmp, k, n, n_threads) : cloudy_oracle_rhs_coal_batch(cfg, tmp, k, n, n_threads);
+        for (size_t i = 0; i < len; ++i) u[i] = (u[i] + 2 * tmp[i] + 2 * dt * k[i]) / 3;
+    }
+    free(k);
+    free(tmp);
     return status;
 }
 

@@ -220,6 +220,8 @@ def moment_source_helper(d: Dist, p1: float, p2: float, x_threshold: float, n_bi
     """ParticleDistributions.jl:557-625."""
     if d.kind == MONODISPERSE:  # :557-564
         return d.n ** 2 * d.p1 ** (p1 + p2) if d.p1 < x_threshold / 2 else 0.0
+    if d.kind == LOGNORMAL and LOGNORMAL_FIXED_RULE is not None:
+        return moment_source_helper_lognormal_closed(d, p1, p2, x_threshold, LOGNORMAL_FIXED_RULE[0], LOGNORMAL_FIXED_RULE[1])
     if d.kind == LOGNORMAL:  # :614-625 — nested adaptive GK (QuadGK default rtol sqrt(eps))
         rt = math.sqrt(EPS)
 
@@ -257,13 +259,24 @@ def moment_source_helper(d: Dist, p1: float, p2: float, x_threshold: float, n_bi
     return n ** 2 * theta ** (p2 - 1) * simpson
 
 
-def moment_source_helper_lognormal_closed(d: Dist, p1: float, p2: float, x_threshold: float, order: int = 96) -> float:
+# When set to (order, top_order), moment_source_helper evaluates Lognormal modes with the fixed closed-form rule below instead
+# of the nested adaptive quadrature: the rule the CUDA path uses (128 points, range up to the mode's top carried order), so
+# that the two implementations of the SAME rule can be compared at rounding level (tests only).
+LOGNORMAL_FIXED_RULE = None
+
+
+def moment_source_helper_lognormal_closed(d: Dist, p1: float, p2: float, x_threshold: float, order: int = 96, top_order=None) -> float:
     """Same integral as ParticleDistributions.jl:614-625 with the inner integral in closed form
      and a fixed Gauss-Legendre outer rule in t = ln y.  Used to quantify the
-    reference's own adaptive-quadrature error; not the reference algorithm."""
+    reference's own adaptive-quadrature error; not the reference algorithm.  ``top_order`` selects the integration range of
+    the CUDA rule: [mu - 12 sigma, min(ln x_th, mu + top_order sigma^2 + 12 sigma)]."""
     n, mu, sig = d.n, d.p1, d.p2
-    lo = mu + p2 * sig ** 2 - 12 * sig
-    hi = math.log(x_threshold)
+    if top_order is None:
+        lo = mu + p2 * sig ** 2 - 12 * sig
+        hi = math.log(x_threshold)
+    else:
+        lo = mu - 12 * sig
+        hi = min(math.log(x_threshold), mu + top_order * sig ** 2 + 12 * sig)
     if hi <= lo:
         return 0.0
     xs, ws = np.polynomial.legendre.leggauss(order)

@@ -333,6 +333,41 @@ def test_lognormal_mode_with_threshold(cb):
         assert ok, (i, worst)
     # mass is conserved whatever the quadrature
     assert np.all(np.abs(got[:, 1] + got[:, 4]) <= 1e-12 * (np.abs(got[:, 1]) + np.abs(got[:, 4]) + 1e-300))
+    # the same fixed rule in the oracle (closed-form inner integral, 128-point Gauss-Legendre up to the top carried order
+    # P + 1): two independent implementations of one rule agree at 1e-11, the 1e-7 above is the distance of that rule (and of
+    # the reference's own adaptive one) from the exact integral
+    O.LOGNORMAL_FIXED_RULE = (128, par.coal_data.P + 1)
+    try:
+        for i in range(24):
+            ref, sc = O.rhs_coal(state[i], opar, return_scale=True)
+            ok, worst = tendency_close(got[i], ref, sc, 1e-11)
+            assert ok, (i, worst)
+    finally:
+        O.LOGNORMAL_FIXED_RULE = None
+
+
+def test_lognormal_moment_source_helper_scalar(cb):
+    """cloudy_moment_source_helper for a Lognormal mode (ParticleDistributions.jl:614-625): the reference's goldens
+    (test_ParticleDistributions_correctness.jl:215-218, rtol 1e-3), the oracle's implementation of the same fixed rule at 1e-11,
+    a converged evaluation of the closed form at 1e-6, and the adaptive restatement at 1e-6"""
+    from cloudy_b200.distributions import LognormalPrimitiveParticleDistribution as LogN
+    d = LogN(1.0, 0.5, 2.0)
+    od = O.Lognormal(1.0, 0.5, 2.0)
+    for (p1, p2, gold) in ((0.0, 0.0, 2.831e-1), (1.0, 0.0, 1.725e-1), (1.0, 1.0, 8.115e-2)):
+        got = cb.moment_source_helper(d, p1, p2, 2.5)
+        assert abs(got - gold) <= 1e-3 * gold
+        assert abs(got - O.moment_source_helper(od, p1, p2, 2.5)) <= 1e-6 * got
+    rng = np.random.default_rng(12)
+    for _ in range(40):
+        mu, sg = rng.uniform(-1.0, 2.0), rng.uniform(0.25, 0.9)
+        T = float(np.exp(rng.uniform(mu - sg, mu + 2.5 * sg)))
+        p1, p2 = sorted(rng.uniform(0.0, 3.0, 2))
+        n = float(np.exp(rng.uniform(-3, 3)))
+        got = cb.moment_source_helper(LogN(n, mu, sg), p1, p2, T)
+        same_rule = O.moment_source_helper_lognormal_closed(O.Lognormal(n, mu, sg), p1, p2, T, order=128, top_order=max(p1, p2, 0.0))
+        assert abs(got - same_rule) <= 1e-11 * abs(same_rule), (mu, sg, T, p1, p2, got, same_rule)
+        converged = O.moment_source_helper_lognormal_closed(O.Lognormal(n, mu, sg), p1, p2, T, order=1200)
+        assert abs(got - converged) <= 1e-6 * abs(converged), (mu, sg, T, p1, p2, got, converged)
 
 
 def test_condensation_batched(cb):

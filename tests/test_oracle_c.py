@@ -5,10 +5,28 @@ from oracle import c_oracle, cloudy_oracle as O
 from tests.oracle_bridge import oracle_params, tendency_close
 
 
-def _cfg(par):
+def _cfg(par, nz=1):
     import cloudy_b200 as cb
     kinds = tuple(d.kind for d in par.pdists)
-    return cb.build_config(kinds, par.coal_data, norms=par.norms)
+    return cb.build_config(kinds, par.coal_data, norms=par.norms, vel=tuple(getattr(par, "vel", ())), dz=getattr(par, "dz", 1.0), nz=nz)
+
+
+def _rain_columns(n_columns, nz, seed):
+    """rainshaft columns with rain content and a few negative entries (the right-hand side clips them in place)"""
+    from cloudy_b200 import workloads as W
+    par, cols = W.c3_rainshaft(n_columns=n_columns, nz=nz)
+    rng = np.random.default_rng(seed)
+    st = cols.copy()
+    shp = st.shape[:-1]
+    frac = rng.uniform(0.0, 2e-3, shp) * (st[..., 1] > 0)
+    th = np.exp(rng.uniform(np.log(1.0), np.log(8.0), shp)) * 1e-9
+    k = rng.uniform(0.8, 3.0, shp)
+    m1 = st[..., 1] * frac
+    st[..., 3] = m1 / (th * k)
+    st[..., 4] = m1
+    st[..., 5] = m1 * th * (k + 1)
+    st[rng.random(st.shape) < 0.02] *= -1e-3
+    return par, np.ascontiguousarray(st)
 
 
 def test_c_oracle_matches_scipy_oracle_c2():
@@ -32,3 +50,44 @@ def test_c_oracle_matches_scipy_oracle_mono_and_long():
             ref, sc = O.rhs_coal(state[i], opar, return_scale=True)
             ok, worst = tendency_close(got[i], ref, sc, 1e-11)
             assert ok, (gen.__name__, worst)
+
+
+def test_c_oracle_sedimentation_and_rainshaft_rhs_match_scipy_oracle():
+    """Sedimentation.jl:22-37 and rainshaft_helpers.jl:47-88 (in-place clip, empty-cell skip, upwind divergence, zero flux on top)"""
+    par, st = _rain_columns(2, 12, seed=4)
+    cfg = _cfg(par, nz=12)
+    opar = oracle_params(par)
+    clipped = np.maximum(st, 0.0)
+    fl = c_oracle.sedimentation_flux_batch(cfg, clipped.reshape(-1, 6))
+    for i in range(0, 24, 3):
+        ref = O.sedimentation_flux_state(clipped.reshape(-1, 6)[i], opar)
+        assert np.allclose(fl[i], ref, rtol=1e-13, atol=0)
+    work = st.copy()
+    got = c_oracle.rainshaft_rhs(cfg, work, n_threads=2)
+    assert np.array_equal(work, clipped)  # clipped in place
+    for c in range(2):
+        col = st[c].copy()
+        ref, sc = O.rainshaft_rhs(col, opar, return_scale=True)
+        ok, worst = tendency_close(got[c], ref, sc, 1e-11)
+        assert ok, worst
+
+
+def test_c_oracle_ssprk33_matches_scipy_oracle_runs():
+    """the same Shu-Osher scheme in both oracles: box model (box_gamma_mixture.jl) and one rainshaft column"""
+    from cloudy_b200 import workloads as W
+    par, state = W.c2_gamma_gamma(n_parcels=3)
+    opar = oracle_params(par)
+    # parcel 0 is the script's own initial condition (dt = 10 s, box_gamma_mixture.jl:23); the random members are much denser
+    # and get a step they are stable with
+    for sel, dt, nsteps in ((slice(0, 1), 10.0, 4), (slice(1, 3), 0.01, 3)):
+        got = c_oracle.ssprk33(_cfg(par), state[sel], dt, nsteps, model=0, n_threads=1)
+        for g, m0 in zip(got, state[sel]):
+            ref = O.ssprk33(lambda m: O.rhs_coal(m, opar), m0, dt, nsteps)
+            assert np.all(np.isfinite(ref))
+            assert np.allclose(g, ref, rtol=1e-9, atol=0), (g, ref)
+    par, st = _rain_columns(1, 10, seed=8)
+    cfg = _cfg(par, nz=10)
+    got = c_oracle.ssprk33(cfg, st, par.dt, 6, model=1, n_threads=2)
+    ref = O.ssprk33(lambda m: O.rainshaft_rhs(m, oracle_params(par)), st[0], par.dt, 6)
+    scale = np.maximum(np.abs(ref), np.abs(ref).max(axis=0, keepdims=True) * 1e-9)
+    assert np.all(np.abs(got[0] - ref) <= 1e-9 * scale), np.max(np.abs(got[0] - ref) / scale)
