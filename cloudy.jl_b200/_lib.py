@@ -85,6 +85,8 @@ SIGNATURES = {
     "cloudy_get_standard_N_q_1": (_P, C.c_int32, _I32, _D, C.c_double, _D),
     "cloudy_integrate_simpson": (_P, C.c_int32, C.c_double, _D, _D),
     "cloudy_measure_fp64_peak": (_P, _D),
+    "cloudy_config_sizeof": (),
+    "cloudy_config_offsets": (_I64, C.c_int32),
 }
 
 _lib = None
@@ -107,8 +109,27 @@ def load():
         fn.restype = C.c_int
     lib.cloudy_last_error.argtypes = []
     lib.cloudy_last_error.restype = C.c_char_p
+    lib.cloudy_config_sizeof.restype = C.c_int64
+    lib.cloudy_config_offsets.restype = C.c_int32
+    check_config_layout(lib)
     _lib = lib
     return lib
+
+
+def config_layout():
+    """(sizeof, [field offsets]) of this module's mirror of ``cloudy_config``"""
+    return C.sizeof(cloudy_config), [getattr(cloudy_config, name).offset for name, _ in cloudy_config._fields_]
+
+
+def check_config_layout(lib):
+    """the library reports sizeof(cloudy_config) and its field offsets as compiled (cloudy_config_sizeof / cloudy_config_offsets):
+    refuse to run with a mirror that has drifted"""
+    size, offs = config_layout()
+    got = (C.c_int64 * 64)()
+    n = lib.cloudy_config_offsets(got, 64)
+    if lib.cloudy_config_sizeof() != size or n != len(offs) or list(got[:n]) != offs:
+        raise ImportError(f"cloudy_config layout mismatch: library sizeof {lib.cloudy_config_sizeof()} offsets {list(got[:n])}, "
+                          f"Python mirror sizeof {size} offsets {offs}")
 
 
 def check(rc):

@@ -17,6 +17,7 @@
 // from the downward recurrence gamma(a,z) = (gamma(a+1,z) + z^a e^-z)/a.  The polynomial-kernel
 // contraction (Q/R/S) runs one output moment per lane from shared memory.  FP64 CUDA cores only.
 #include <cuda_runtime.h>
+#include <cstddef>
 #include <dlfcn.h>
 #include <math.h>
 #include <stdint.h>
@@ -2588,6 +2589,23 @@ int cloudy_get_cond_evap_1(cloudy_ctx* ctx, int32_t n_modes, const int32_t* kind
 int cloudy_get_standard_N_q_1(cloudy_ctx* ctx, int32_t n_modes, const int32_t* kinds, const double* params, double size_cutoff,
                               double* out) {
     return aux_single(ctx, n_modes, kinds, params, true, 0.0, 0.0, 1000.0, size_cutoff, out);
+}
+
+int64_t cloudy_config_sizeof(void) { return (int64_t)sizeof(cloudy_config); }
+
+int32_t cloudy_config_offsets(int64_t* offsets, int32_t max_fields) {
+    const int64_t off[] = {
+        (int64_t)offsetof(cloudy_config, n_modes), (int64_t)offsetof(cloudy_config, P), (int64_t)offsetof(cloudy_config, kind),
+        (int64_t)offsetof(cloudy_config, nprog), (int64_t)offsetof(cloudy_config, threshold_style), (int64_t)offsetof(cloudy_config, n_mom_max),
+        (int64_t)offsetof(cloudy_config, n_2d_ints), (int64_t)offsetof(cloudy_config, n_bins), (int64_t)offsetof(cloudy_config, n_vel),
+        (int64_t)offsetof(cloudy_config, nz), (int64_t)offsetof(cloudy_config, bins_per_log_unit), (int64_t)offsetof(cloudy_config, reserved),
+        (int64_t)offsetof(cloudy_config, c), (int64_t)offsetof(cloudy_config, thresholds), (int64_t)offsetof(cloudy_config, x_min),
+        (int64_t)offsetof(cloudy_config, dx), (int64_t)offsetof(cloudy_config, norms), (int64_t)offsetof(cloudy_config, k_range),
+        (int64_t)offsetof(cloudy_config, vel), (int64_t)offsetof(cloudy_config, dz)};
+    const int32_t n = (int32_t)(sizeof(off) / sizeof(off[0]));
+    if (!offsets) return n;
+    for (int32_t i = 0; i < n && i < max_fields; ++i) offsets[i] = off[i];
+    return n < max_fields ? n : max_fields;
 }
 
 int cloudy_measure_fp64_peak(cloudy_ctx* ctx, double* tflops) {

@@ -227,6 +227,14 @@ int cloudy_integrate_simpson(cloudy_ctx* ctx, int32_t n_bins, double dx, const d
  * roofline denominator that MEASURED_PEAKS.json lacks */
 int cloudy_measure_fp64_peak(cloudy_ctx* ctx, double* tflops);
 
+/* ---- binding self-check ------------------------------------------------------------------------ */
+/* sizeof(cloudy_config) and the byte offsets of its 20 fields in declaration order, as this library was compiled.  A language
+ * binding that mirrors the struct (julia/CloudyB200.jl CloudyConfig, cloudy.jl_b200/_lib.py) compares them with its own
+ * layout when it loads the library, so the two cannot drift apart silently.  Returns the number of fields written
+ * (at most max_fields). */
+int64_t cloudy_config_sizeof(void);
+int32_t cloudy_config_offsets(int64_t* offsets, int32_t max_fields);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,3 +110,36 @@ def test_workload_generators_are_seeded():
     assert abs((a == 0).all(axis=1).mean() - 0.02) < 0.02
     par, cols = W.c3_rainshaft(4, 32)
     assert cols.shape == (4, 32, 6) and par.dz == 3000.0 / 32
+
+
+def test_julia_config_struct_mirrors_the_library_layout():
+    """julia/CloudyB200.jl cannot run here, but its `struct CloudyConfig` can be read: field names, order and C layout (Int32 /
+    Float64 scalars and NTuples) must equal what the library reports (cloudy_config_sizeof / cloudy_config_offsets) and what the
+    ctypes mirror declares — the two bindings cannot drift apart."""
+    from cloudy_b200 import _lib
+    src = open(os.path.join(ROOT, "julia", "CloudyB200.jl")).read()
+    consts = {"MAX_MODES": _lib.MAX_MODES, "MAX_P": _lib.MAX_P, "MAX_VEL": _lib.MAX_VEL}
+    m = re.search(r"const MAX_MODES, MAX_P, MAX_VEL = (\d+), (\d+), (\d+)", src)
+    assert m and tuple(int(g) for g in m.groups()) == (_lib.MAX_MODES, _lib.MAX_P, _lib.MAX_VEL)
+    body = re.search(r"struct CloudyConfig\n(.*?)\nend", src, re.S).group(1)
+    fields = []
+    for line in body.splitlines():
+        line = line.split("#")[0].strip()
+        if not line:
+            continue
+        name, typ = line.split("::")
+        mt = re.fullmatch(r"NTuple\{(.+),(Int32|Float64)\}", typ)
+        count, base = (eval(mt.group(1), {}, consts), mt.group(2)) if mt else (1, typ)
+        fields.append((name, count, {"Int32": 4, "Float64": 8}[base]))
+    assert [f[0] for f in fields] == [n for n, _ in _lib.cloudy_config._fields_]
+    offs, off = [], 0
+    for _, count, size in fields:          # C layout rule: align every field to its element size
+        off = (off + size - 1) // size * size
+        offs.append(off)
+        off += count * size
+    total = (off + 7) // 8 * 8
+    lib = _lib.load()
+    got = (ctypes.c_int64 * 64)()
+    n = lib.cloudy_config_offsets(got, 64)
+    assert n == len(fields) and list(got[:n]) == offs
+    assert lib.cloudy_config_sizeof() == total == ctypes.sizeof(_lib.cloudy_config)
