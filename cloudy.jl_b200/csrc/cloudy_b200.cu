@@ -727,6 +727,9 @@ __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevCo
         for (int i = 0; i < MAXN; ++i) {
             pn[i] = 0.0; pa[i] = 1.0; pb[i] = 1.0;
             if (i >= cfg.N) continue;
+            // a mode without number or mass (most cells of a column: exact zeros, or clipped negatives) is the empty-mode fallback of
+            // update_dist_from_moments (n = 0) whatever the normalisation: no divisions, no flux
+            if (!(raw[i][0] > 0.0) || !(raw[i][1] > 0.0)) continue;
             const int s0 = cfg.slot0[i], np = cfg.nprog[i], kind = cfg.kind[i];
             double mn[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -921,6 +924,10 @@ __global__ void __launch_bounds__(256) regime_key_kernel(const __grid_constant__
                     const int zi = (zc >= 0.f) ? (int)fminf(zc, (float)(kSerZ - 1)) : 0;
                     const unsigned int deg = sdeg[zi][ai];
                     sub = (flag ? 1u : 0u) | (((deg >> 3) & 7u) << 1);
+                    // FixedThreshold parcels in the continued-fraction regime all have the top series degree: their three bits
+                    // carry how far x_th/θ lies beyond the series limit instead (buckets of 8), which fixes the depth of the
+                    // continued fraction node by node (kCfDepthZ) — warps then agree on the depth as well
+                    if (flag && cfg.thr_style != CLOUDY_MOVING_THRESHOLD) sub = 1u | ((unsigned int)fminf((X - ser_lim) * 0.125f, 7.f) << 1);
                     sub = sub == 0 ? 2u : sub;  // keep 0 for "empty mode"
                 }
                 key |= sub << (4 * used);

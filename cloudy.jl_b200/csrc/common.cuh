@@ -84,6 +84,32 @@ struct ModeParams {
     int invalid;
 };
 
+// Lognormal branch of params_from_moments, kept OUT OF LINE: the hot kernels carry it for every mode (the kind is a run-time
+// value) although the BASELINE configurations never execute it, and its two logarithms, square roots and exponential would
+// otherwise sit in the middle of the instruction stream (instruction-cache footprint)
+static __device__ __noinline__ ModeParams lognormal_params_from_moments(double m0, double m1, double m2, double lo, double hi, double lo2, double hi2) {
+    ModeParams r;
+    r.invalid = 0;
+    if (m0 > kEps && m1 > kEps && m2 > kEps) {
+        // lo/hi clamp μ, lo2/hi2 clamp σ (reference defaults (-Inf, Inf), (eps, Inf))
+        double mu = jl_max(lo, jl_min(hi, log(m1 * m1 / (m0 * sqrt(m0)) / sqrt(m2))));
+        double arg = log(m0 * m2 / (m1 * m1));
+        if (arg < 0.0) r.invalid = 1;  // the reference throws a DomainError here (:498)
+        double sg = jl_max(lo2, jl_min(hi2, sqrt(arg)));
+        r.a = mu;
+        r.b = sg;
+        r.n = m1 / exp(mu + 0.5 * sg * sg);
+    } else {
+        r.n = 0.0; r.a = 1.0; r.b = 1.0;
+    }
+    return r;
+}
+// IEEE division kept out of line where it is evaluated once per parcel and slot (stage update): every inlined FP64 division
+// costs ~100 instructions of code with its slow path
+static __device__ __noinline__ double div_rn_outofline(double a, double b) { return a / b; }
+// moment(Lognormal, q) for integer q (moment matrix), out of line for the same reason
+static __device__ __noinline__ double lognormal_moment_int(double n, double mu, double sg, int q) { return n * exp(q * mu + (double)(q * q) * sg * sg / 2); }
+
 __device__ inline ModeParams params_from_moments(int kind, double m0, double m1, double m2, double lo, double hi,
                                                  double lo2 = kEps, double hi2 = INFINITY) {
     ModeParams r;
@@ -99,18 +125,7 @@ __device__ inline ModeParams params_from_moments(int kind, double m0, double m1,
             r.n = 0.0; r.a = 1.0; r.b = 1.0;
         }
     } else if (kind == CLOUDY_LOGNORMAL) {
-        if (m0 > kEps && m1 > kEps && m2 > kEps) {
-            // lo/hi clamp μ, lo2/hi2 clamp σ (reference defaults (-Inf, Inf), (eps, Inf))
-            double mu = jl_max(lo, jl_min(hi, log(m1 * m1 / (m0 * sqrt(m0)) / sqrt(m2))));
-            double arg = log(m0 * m2 / (m1 * m1));
-            if (arg < 0.0) r.invalid = 1;  // the reference throws a DomainError here (:498)
-            double sg = jl_max(lo2, jl_min(hi2, sqrt(arg)));
-            r.a = mu;
-            r.b = sg;
-            r.n = m1 / exp(mu + 0.5 * sg * sg);
-        } else {
-            r.n = 0.0; r.a = 1.0; r.b = 1.0;
-        }
+        r = lognormal_params_from_moments(m0, m1, m2, lo, hi, lo2, hi2);
     } else {  // Exponential, Monodisperse
         if (m0 > kEps && m1 > kEps) {
             r.n = m0; r.a = m1 / m0; r.b = 1.0;

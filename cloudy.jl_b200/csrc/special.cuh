@@ -268,6 +268,32 @@ static __constant__ unsigned char kSeriesDeg2[kSerZ][kSerA] = {
 static __constant__ double kSeriesLimit[kSerA] = {18.0, 18.0, 19.0, 19.0, 20.0, 20.0, 21.0, 21.0, 22.0, 22.0, 23.0, 23.0, 24.0, 25.0, 25.0, 26.0, 26.0, 26.0};
 static __constant__ int kCfDepth[kSerA] = {4, 4, 5, 5, 6, 6, 7, 8, 9, 10, 10, 11, 11, 12, 13, 13, 14, 15};
 
+// Depth of the same continued fraction as a function of z: rows floor(a) = 0..17, columns z in [limit + 4b, limit + 4b + 4), last
+// column everything beyond.  Smallest depth with |Q_d - Q| <= 1e-16 (error relative to the lower function), generated by
+// tools/gen_cf_depth.py (40-digit mpmath); the kernels add one level of margin to every non-zero entry.  The fraction
+// converges quickly once z >> a: beyond limit + 16 half the depth of kCfDepth is enough, beyond limit + 44 none.
+constexpr int kCfZBins = 16;
+static __constant__ unsigned char kCfDepthZ[kSerA][kCfZBins] = {
+    { 3,  2,  1,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0},
+    { 3,  2,  1,  1,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0},
+    { 4,  3,  2,  1,  1,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0},
+    { 4,  3,  3,  2,  1,  1,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0},
+    { 5,  4,  3,  3,  2,  1,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0},
+    { 5,  5,  4,  3,  2,  1,  1,  0,  0,  0,  0,  0,  0,  0,  0,  0},
+    { 6,  5,  4,  3,  3,  2,  1,  0,  0,  0,  0,  0,  0,  0,  0,  0},
+    { 7,  6,  5,  4,  3,  2,  1,  1,  0,  0,  0,  0,  0,  0,  0,  0},
+    { 8,  7,  6,  4,  3,  3,  2,  1,  0,  0,  0,  0,  0,  0,  0,  0},
+    { 9,  7,  6,  5,  4,  3,  2,  1,  1,  0,  0,  0,  0,  0,  0,  0},
+    { 9,  8,  7,  5,  4,  3,  2,  2,  1,  0,  0,  0,  0,  0,  0,  0},
+    {10,  9,  7,  6,  5,  4,  3,  2,  1,  0,  0,  0,  0,  0,  0,  0},
+    {10,  9,  8,  6,  5,  4,  3,  2,  1,  1,  0,  0,  0,  0,  0,  0},
+    {11,  9,  8,  7,  5,  4,  3,  2,  2,  1,  0,  0,  0,  0,  0,  0},
+    {12, 10,  9,  7,  6,  5,  4,  3,  2,  1,  1,  0,  0,  0,  0,  0},
+    {12, 11,  9,  8,  6,  5,  4,  3,  2,  1,  1,  0,  0,  0,  0,  0},
+    {13, 11, 10,  8,  7,  6,  5,  4,  3,  2,  1,  0,  0,  0,  0,  0},
+    {14, 12, 11,  9,  8,  6,  5,  4,  3,  2,  1,  1,  0,  0,  0,  0},
+};
+
 __device__ __forceinline__ int series_z_bin(double zmax) { return (zmax >= 0.0) ? (int)fmin(zmax, (double)(kSerZ - 1)) : 0; }
 __device__ __forceinline__ int series_a_bin(double a_top) { return (int)fmin(fmax(a_top, 0.0), (double)(kSerA - 1)); }
 

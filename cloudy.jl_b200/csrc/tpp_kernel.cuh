@@ -403,7 +403,7 @@ __device__ __forceinline__ void tpp_block_tail(double (&top)[P + 1], double (&Z)
 #pragma unroll
     for (int i = 0; i < NPL; ++i) {
         const double gE = fast_exp(fma(k, ls[i], e0), exp_tab);  // g_j * E_j
-        const double hs = (z[i] < cf_lim) ? h[i] : 0.0;          // continued-fraction nodes are added by the rare loop
+        const double hs = (z[i] < cf_lim) ? h[i] : 0.0;          // continued-fraction nodes are added by the rare loop (a warp-uniform branch here measured 1 % slower)
         const double zh = z[i] * hs;
         double w[P1 + 1];
 #pragma unroll
@@ -482,8 +482,8 @@ struct FixedGrid {
 template <int MP, int P>
 __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2], const FixedGrid grid, const double k,
                                                  const double inv_th, const double log_th, const double X, const double gam_top,
-                                                 const double (&ia)[MP], double* __restrict__ myCt, const int deg, const int cfd_w,
-                                                 const int cfd, const double a_top, const double ser_lim,
+                                                 const double (&ia)[MP], double* __restrict__ myCt, const int deg,
+                                                 const unsigned char* __restrict__ cfdz, const double a_top, const double ser_lim,
                                                  const double* __restrict__ exp_tab) {
     static_assert(MP == P + 2, "all M = P + 2 orders are carried");
     constexpr int T = MP * (MP + 1) / 2;
@@ -555,11 +555,16 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
         }
     }
     // ---- near nodes: Taylor polynomial about X_c, degree by node block ----
+    // Two loops, chosen per warp, so that the common one stays compact in the instruction cache: (1) no parcel of the warp has
+    // its centre capped: compile-time degrees; (2) some parcel is capped at the series limit: it sees |r| up to 0.1 at EVERY
+    // near node (r no longer vanishes with x_j/x_th) and takes the full degree, its warp-mates keep their own degree by
+    // predication (same operations as in loop 1, so a parcel's result does not depend on the loop its warp runs).
     const int n_near_b = grid.n_near / NPL;
-    for (int bt = 0; bt < n_near_b; ++bt) {
-        const double2* __restrict__ rb = reinterpret_cast<const double2*>(grid.rec + bt * NPL * S2);
-        const int Kj = (int)grid.kblk[bt];  // node-only degree: the same for every parcel
-        if (!warp_capped) {
+    constexpr int CAP_UNROLL = (P >= 4) ? TPP_TAYLOR_MAX + 1 : 1;
+    if (!warp_capped) {
+        for (int bt = 0; bt < n_near_b; ++bt) {
+            const double2* __restrict__ rb = reinterpret_cast<const double2*>(grid.rec + bt * NPL * S2);
+            const int Kj = (int)grid.kblk[bt];  // node-only degree: the same for every parcel
             double z[NPL], h[NPL], ls[NPL], r[NPL];
 #pragma unroll
             for (int i = 0; i < NPL; ++i) {
@@ -576,9 +581,11 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
             }
 #undef TPP_NEAR_CASE
             tpp_block_tail<MP, P, NPL>(top, Z, rb, z, h, ls, k, e0, cf_lim, exp_tab);
-        } else {
-            // a parcel whose centre is capped at the series limit sees |r| up to 0.1 at EVERY near node (r no longer
-            // vanishes with x_j/x_th): it takes the full degree; its warp-mates keep their own degree by predication
+        }
+    } else {
+        for (int bt = 0; bt < n_near_b; ++bt) {
+            const double2* __restrict__ rb = reinterpret_cast<const double2*>(grid.rec + bt * NPL * S2);
+            const int Kj = (int)grid.kblk[bt];
             double z[NPL], h[NPL], ls[NPL], r[NPL];
 #pragma unroll
             for (int i = 0; i < NPL; ++i) {
@@ -589,6 +596,9 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
                 h[i] = 0.0;
             }
             const int Kown = capped ? TPP_TAYLOR_MAX : Kj;
+            // unrolled for the high-order tensors only: rolled, this loop costs C4 (a quarter of its parcels is capped) 40 %;
+            // unrolled, its code costs C5 (no capped parcel) 2 % through the instruction cache
+#pragma unroll CAP_UNROLL
             for (int m = TPP_TAYLOR_MAX; m >= 0; --m) {
                 const double tm = myCt[m * TPP_THREADS];
                 if (m <= Kown) {
@@ -596,7 +606,7 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
                     for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], r[i], tm);
                 }
             }
-            tpp_block_tail<MP, P, tpp_npl(P)>(top, Z, rb, z, h, ls, k, e0, cf_lim, exp_tab);
+            tpp_block_tail<MP, P, NPL>(top, Z, rb, z, h, ls, k, e0, cf_lim, exp_tab);
         }
     }
     // downward recurrence of the sums; only entries with p1 + p2 <= 2P are ever read by the S terms
@@ -636,11 +646,14 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
             const double zc = fmin(z, 256.0);  // beyond this the upper function is < 1e-80 of Gamma(a)
             double b = zc + 1.0 - a_top;
             double Pm = 1.0, Pc = b, Qm = 0.0, Qc = 1.0, fn = 0.0;
-            for (int n = 1; n <= cfd_w; ++n) {
+            // depth by (a, z): the fraction needs fewer levels the further z lies beyond the series limit (kCfDepthZ)
+            const int dj = cf_j ? (int)cfdz[(int)fmin(fmax((zc - ser_lim) * 0.25, 0.0), (double)(kCfZBins - 1))] : 0;
+            const int dj_w = __reduce_max_sync(0xffffffffu, dj);
+            for (int n = 1; n <= dj_w; ++n) {
                 // beyond the parcel's own depth the step degenerates to P <- 1*P + 0, which is exact
                 fn += 1.0;
                 b += 2.0;
-                const bool on = n <= cfd;
+                const bool on = n <= dj;
                 const double an = on ? fn * (a_top - fn) : 0.0;  // -n(n-a)
                 const double bb = on ? b : 1.0;
                 const double Pn = fma(bb, Pc, an * Pm);
@@ -673,7 +686,7 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
 //   n exp(p1 μ + p1² σ²/2) Φ((ln(T-y) - μ - p1 σ²)/σ), outer integral by a fixed Gauss-Legendre rule in t = ln y.
 // (The reference nests two adaptive QuadGK calls at rtol sqrt(eps); this rule agrees with it to ~1e-10.)
 template <int MP>
-__device__ __forceinline__ void tpp_lognormal_H(double (&acc)[MP * (MP + 1) / 2], const double* __restrict__ gl, const int gl_n, const double n,
+__device__ __noinline__ void tpp_lognormal_H(double (&acc)[MP * (MP + 1) / 2], const double* __restrict__ gl, const int gl_n, const double n,
                                                 const double mu, const double sg, const double Tthr) {
     constexpr int T = MP * (MP + 1) / 2;
 #pragma unroll
@@ -746,6 +759,7 @@ struct TppShared {
     double serlim[kSerA];
     double exp32[TPP_EXP_TAB];  // 2^(i/256)
     int cfd[kSerA];
+    unsigned char cfdz[kSerA][kCfZBins];  // continued-fraction depth by (floor(a), z bin), margin included
     unsigned char kdeg_m[128];  // MovingThreshold own grids: Taylor degree bound of node m (counted from the threshold)
 };
 
@@ -765,6 +779,10 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
     for (int i = tid; i < st_total; i += TPP_THREADS) sTab[i] = cfg.tab[st_off + i];
     for (int i = tid; i < kSerZ * kSerA; i += TPP_THREADS) sh.deg[i / kSerA][i % kSerA] = kSeriesDeg2[i / kSerA][i % kSerA];
     if (tid < kSerA) { sh.cfd[tid] = kCfDepth[tid]; sh.serlim[tid] = kSeriesLimit[tid]; }
+    for (int i = tid; i < kSerA * kCfZBins; i += TPP_THREADS) {
+        const int dz_ = kCfDepthZ[i / kCfZBins][i % kCfZBins];
+        sh.cfdz[i / kCfZBins][i % kCfZBins] = (unsigned char)(dz_ > 0 ? dz_ + 1 : 0);
+    }
     for (int i = tid; i < TPP_EXP_TAB; i += TPP_THREADS) sh.exp32[i] = exp2((double)i / (double)TPP_EXP_TAB);
     if (MOVING && tid < 128) {
         // same degree rule as the host's table grid (cloudy_config_set): |r| <= 1.15 ρ, ρ_m <= 10^(-m/bins_per_log_unit)
@@ -786,17 +804,21 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
         const long long q = (ix < n) ? ix : n - 1;
         return (args.perm != nullptr) ? (long long)args.perm[q] : q;
     };
+#ifdef TPP_PREFETCH_REGS
     double nxt[N][3];
+#endif
     long long p_next = 0;
     {
         const long long b0 = blockIdx.x * (long long)TPP_THREADS + (tid & ~31);
         if (b0 < n) {
             p_next = parcel_of(b0);
+#ifdef TPP_PREFETCH_REGS
 #pragma unroll
             for (int i = 0; i < N; ++i)
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
                     nxt[i][q] = (q < cfg.nprog[i]) ? args.u_in[(cfg.slot0[i] + q) * args.s_in + p_next * args.ps_in] : 0.0;
+#endif
         }
     }
     for (long long base = blockIdx.x * (long long)TPP_THREADS + (tid & ~31); base < n; base += stride_all) {
@@ -804,6 +826,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
         const bool live = idx < n;
         const long long p = p_next;
         double cur[N][3];
+#ifdef TPP_PREFETCH_REGS
 #pragma unroll
         for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -815,6 +838,40 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
                     nxt[i][q] = (q < cfg.nprog[i]) ? args.u_in[(cfg.slot0[i] + q) * args.s_in + p_next * args.ps_in] : 0.0;
+        }
+#else
+        // this parcel's moments (requested one iteration ago with an L2 prefetch: holding the NEXT parcel's values in registers
+        // across the node loops made the 128-register instances spill them, and the spill store waits for the DRAM load)
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                cur[i][q] = (q < cfg.nprog[i]) ? args.u_in[(cfg.slot0[i] + q) * args.s_in + p * args.ps_in] : 0.0;
+        if (base + stride_all < n) {
+            p_next = parcel_of(base + stride_all);
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    if (q < cfg.nprog[i])
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(args.u_in + (cfg.slot0[i] + q) * args.s_in + p_next * args.ps_in));
+        }
+#endif
+        // zero flux above the column top (rainshaft_helpers.jl:80-81); one 64-bit modulo per cell
+        const bool top_level = RAIN && ((p + 1) % cfg.nz == 0);
+        if constexpr (RAIN) {
+            // the sedimentation fluxes of this cell and of the cell above are read at the very end: request them now
+            if (live && args.flux != nullptr) {
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+                        if (q < cfg.nprog[i]) {
+                            const double* fp = args.flux + (cfg.slot0[i] + q) * args.s_flux + p;
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(fp));
+                            if (!top_level) asm volatile("prefetch.global.L1 [%0];" ::"l"(fp + 1));
+                        }
+            }
         }
 
         // ---- load, (clip), normalise, parameters, moment matrix --------------------------------------
@@ -853,7 +910,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
 #pragma unroll
             for (int q = 0; q < M; ++q) {  // Coalescence.jl:187-198
                 double val = mq;
-                if (kind == CLOUDY_LOGNORMAL) val = mp.n * exp(q * mp.a + (double)(q * q) * mp.b * mp.b / 2);
+                if (kind == CLOUDY_LOGNORMAL) val = lognormal_moment_int(mp.n, mp.a, mp.b, q);
                 mom[i][q] = (q < cfg.n_mom_max) ? val : 0.0;
                 if (kind == CLOUDY_GAMMA) mq *= mp.a * (mp.b + q);
                 else if (kind == CLOUDY_EXPONENTIAL) mq *= mp.a * (q + 1.0);
@@ -1048,7 +1105,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                                 fg.n_far = cfg.rec2_far[i];
                                 fg.soa = cfg.tab + cfg.tab_off[i];
                                 fg.nb = cfg.n_bins[i];
-                                tpp_nodes_fixed2<MP, P>(F, fg, k, inv_th, log(th), X, gam_top, ia, myCt, deg, cfd_w, cfd, a_top, ser_lim, sh.exp32);
+                                tpp_nodes_fixed2<MP, P>(F, fg, k, inv_th, log(th), X, gam_top, ia, myCt, deg, sh.cfdz[ai], a_top, ser_lim, sh.exp32);
                             }
                             double thp[MP];  // H = n^2 θ^{p2}/Γ(k)^2 * sum
                             thp[0] = pre0;
@@ -1130,7 +1187,6 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
         }  // !warp_idle
 
         // ---- assemble, combine with the stage update, store ---------------------------------------------
-        const bool top_level = RAIN && ((p + 1) % cfg.nz == 0);  // zero flux above the column top (rainshaft_helpers.jl:80-81)
         const double inv_dz = 1.0 / cfg.dz;
 #pragma unroll
         for (int k = 0; k < N; ++k) {
@@ -1161,7 +1217,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                             if (RAIN) un = (un < 0.0) ? 0.0 : un;
                             acc2 = args.cn * un + acc2;
                         }
-                        o = (acc2 + args.cf * (args.dt * f)) / args.div;
+                        o = div_rn_outofline(acc2 + args.cf * (args.dt * f), args.div);
                         if (RAIN) o = (o < 0.0) ? 0.0 : o;
                     }
                     args.out[s * args.s_out + p * args.ps_out] = o;
