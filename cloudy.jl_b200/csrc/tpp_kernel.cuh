@@ -21,7 +21,10 @@ namespace cloudy {
 constexpr int TPP_THREADS = 128;
 // nodes in flight per thread (measured on C2, P = 2: 2 → 0.70 ms, 3 → 0.66, 4 → 0.74, 5 → 0.73); high-order tensors carry
 // up to 28 accumulators per node set, so they keep fewer nodes in flight
-__host__ __device__ constexpr int tpp_npl(int P) { return (void)P, 3; }  // (2 for P >= 4 measured within noise: +4 % at 1 Mi, -4 % at 16 Mi parcels on C4)
+#ifndef TPP_NPL_LARGE
+#define TPP_NPL_LARGE 3
+#endif
+__host__ __device__ constexpr int tpp_npl(int P) { return P >= 4 ? TPP_NPL_LARGE : 3; }  // (2 for P >= 4 measured within noise: +4 % at 1 Mi, -4 % at 16 Mi parcels on C4)
 // resident blocks per SM the register allocation must allow (168 registers for 3 blocks of 128 threads): the small shapes
 // fit, the others take up to 255 registers and run 2 blocks
 #ifndef TPP_MINB_SMALL
