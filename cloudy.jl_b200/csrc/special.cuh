@@ -224,6 +224,18 @@ __device__ __forceinline__ double gamma_shape(double k) {
     return exp(lg) / (pa * pb);
 }
 
+// 1/Gamma(k) by the same formulas without the division (the FixedThreshold node loop needs n^2/Gamma(k)^2 only)
+__device__ __forceinline__ double gamma_shape_inv(double k) {
+    const double x = k + 12.0;
+    const double lg = fma(x - 0.5, log(x), -x) + (0.9189385332046727 + stirling_tail(x));
+    double pa = k * (k + 1.0), pb = (k + 2.0) * (k + 3.0);
+    pa *= (k + 4.0) * (k + 5.0);
+    pb *= (k + 6.0) * (k + 7.0);
+    pa *= (k + 8.0) * (k + 9.0);
+    pb *= (k + 10.0) * (k + 11.0);
+    return exp(-lg) * (pa * pb);
+}
+
 // standard normal CDF
 __device__ __forceinline__ double norm_cdf(double t) { return 0.5 * erfc(-t * 0.7071067811865476); }
 

@@ -484,7 +484,7 @@ struct FixedGrid {
 // downward recurrence runs ONCE per parcel after the loop instead of once per node.
 template <int MP, int P>
 __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2], const FixedGrid grid, const double k,
-                                                 const double inv_th, const double log_th, const double X, const double gam_top,
+                                                 const double inv_th, const double log_th, const double X, const double poch_top, const double inv_gk,
                                                  const double (&ia)[MP], double* __restrict__ myCt, const int deg,
                                                  const unsigned char* __restrict__ cfdz, const double a_top, const double ser_lim,
                                                  const double* __restrict__ exp_tab) {
@@ -628,6 +628,7 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
 
     // ---- rare path: nodes in the continued-fraction regime (only when x_th/θ reaches the series limit) ----
     if (warp_cf) {
+        const double gam_top = poch_top / inv_gk;  // Γ(k+MP-1) = Γ(k) (k)_{MP-1}
         double B[MP];
         B[MP - 1] = 1.0;
 #pragma unroll
@@ -979,7 +980,9 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                         finish_ln(std::integral_constant<int, M>{});
                     } else {
                         const double inv_th = 1.0 / th;
-                        const double gk = (cfg.kind[i] == CLOUDY_GAMMA) ? gamma_shape(k) : 1.0;
+                        // Gamma(k): the MovingThreshold instances need it itself (inverse incomplete gamma), the others only 1/Gamma(k)
+                        const double inv_gk = MOVING ? 1.0 : ((cfg.kind[i] == CLOUDY_GAMMA) ? gamma_shape_inv(k) : 1.0);
+                        const double gk = MOVING ? ((cfg.kind[i] == CLOUDY_GAMMA) ? gamma_shape(k) : 1.0) : 1.0;
                         // All M orders are carried even when N_2d_ints[i] = M - 1 (two adjacent 2-moment modes): the downward
                         // recurrence from the higher top order gives the same lower orders, the unused top entries are masked in
                         // `contract`, and the node loop exists once per mode instead of twice (code size)
@@ -1042,17 +1045,24 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                             else myCt[0] = cc;
                             for (int nn = deg + 1; nn <= deg_w; ++nn) myCt[nn * TPP_THREADS] = 0.0;
                         }
-                        const double pre0 = nmd * nmd / (gk * gk);
+                        const double pre0 = MOVING ? nmd * nmd / (gk * gk) : (nmd * inv_gk) * (nmd * inv_gk);
                         auto finish = [&](auto mp_tag) {
                             constexpr int MP = decltype(mp_tag)::value;
-                            double ia[MP];
-                            double gam_top = gk;
+                            // ia[p] = 1/(k+p) for p < MP-1 from ONE division (prefix and suffix products; k >= eps keeps the product
+                            // normal); Γ(k+MP-1) = Γ(k) (k)_{MP-1} is needed by the continued-fraction path only
+                            double ia[MP], pre[MP], suf[MP];
+                            pre[0] = 1.0;
 #pragma unroll
-                            for (int pp = 0; pp < MP - 1; ++pp) {
-                                ia[pp] = 1.0 / (k + (double)pp);
-                                gam_top *= (k + (double)pp);  // Γ(k+MP-1)
-                            }
+                            for (int pp = 1; pp < MP; ++pp) pre[pp] = pre[pp - 1] * (k + (double)(pp - 1));  // pre[p] = prod_{q<p}(k+q)
+                            suf[MP - 1] = 1.0; suf[MP - 2] = 1.0;
+#pragma unroll
+                            for (int pp = MP - 3; pp >= 0; --pp) suf[pp] = suf[pp + 1] * (k + (double)(pp + 1));  // prod_{p<q<MP-1}(k+q)
+                            const double poch = pre[MP - 1];  // (k)_{MP-1}
+                            const double inv_poch_k = 1.0 / poch;
+#pragma unroll
+                            for (int pp = 0; pp < MP - 1; ++pp) ia[pp] = inv_poch_k * (pre[pp] * suf[pp]);
                             ia[MP - 1] = 0.0;
+                            const double gam_top = MOVING ? gk * poch : poch;  // FixedThreshold: divided by inv_gk where it is used
                             double F[MP * (MP + 1) / 2];
 #pragma unroll
                             for (int t = 0; t < MP * (MP + 1) / 2; ++t) F[t] = 0.0;
@@ -1108,7 +1118,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                                 fg.n_far = cfg.rec2_far[i];
                                 fg.soa = cfg.tab + cfg.tab_off[i];
                                 fg.nb = cfg.n_bins[i];
-                                tpp_nodes_fixed2<MP, P>(F, fg, k, inv_th, log(th), X, gam_top, ia, myCt, deg, sh.cfdz[ai], a_top, ser_lim, sh.exp32);
+                                tpp_nodes_fixed2<MP, P>(F, fg, k, inv_th, log(th), X, gam_top, inv_gk, ia, myCt, deg, sh.cfdz[ai], a_top, ser_lim, sh.exp32);
                             }
                             double thp[MP];  // H = n^2 θ^{p2}/Γ(k)^2 * sum
                             thp[0] = pre0;
