@@ -1413,7 +1413,7 @@ static int sort_buffer(cloudy_ctx* ctx, const double* in, double* out, long long
 // move a state's parcels into regime order (the device buffer is exchanged with the context's scratch ensemble)
 static int regime_sort_state(cloudy_ctx* ctx, cloudy_state* st) {
     if (st->n == 0) return CLOUDY_OK;
-    if (!ctx->sort_scratch || ctx->sort_scratch->n != st->n) {
+    if (!ctx->sort_scratch || ctx->sort_scratch->n != st->n || ctx->sort_scratch->nslots != st->nslots) {
         if (ctx->sort_scratch) { cloudy_state_destroy(ctx->sort_scratch); ctx->sort_scratch = nullptr; }
         int rc = cloudy_state_create(ctx, st->n, &ctx->sort_scratch);
         if (rc) return rc;
@@ -1873,6 +1873,8 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
     for (int i = 0; i < 3; ++i)
         if (ctx->tmp[i]) { cloudy_state_destroy(ctx->tmp[i]); ctx->tmp[i] = nullptr; }
     if (ctx->flux) { cloudy_state_destroy(ctx->flux); ctx->flux = nullptr; }
+    // the sort scratch ensemble has the previous configuration's slot count
+    if (ctx->sort_scratch) { cloudy_state_destroy(ctx->sort_scratch); ctx->sort_scratch = nullptr; }
     return CLOUDY_OK;
 }
 

@@ -14,6 +14,7 @@
 // Warps are made homogeneous (similar series length, same series/continued-fraction regime) by an optional
 // regime sort of the parcel order (args.perm).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace cloudy {
@@ -24,7 +25,10 @@ constexpr int TPP_THREADS = 128;
 #ifndef TPP_NPL_LARGE
 #define TPP_NPL_LARGE 3
 #endif
-__host__ __device__ constexpr int tpp_npl(int P) { return P >= 4 ? TPP_NPL_LARGE : 3; }  // (2 for P >= 4 measured within noise: +4 % at 1 Mi, -4 % at 16 Mi parcels on C4)
+#ifndef TPP_NPL_SMALL
+#define TPP_NPL_SMALL 3
+#endif
+__host__ __device__ constexpr int tpp_npl(int P) { return P >= 4 ? TPP_NPL_LARGE : TPP_NPL_SMALL; }  // (2 for P >= 4 measured within noise: +4 % at 1 Mi, -4 % at 16 Mi parcels on C4)
 // resident blocks per SM the register allocation must allow (168 registers for 3 blocks of 128 threads): the small shapes
 // fit, the others take up to 255 registers and run 2 blocks
 #ifndef TPP_MINB_SMALL
@@ -432,15 +436,20 @@ __device__ __forceinline__ void tpp_block_tail(double (&top)[P + 1], double (&Z)
 // Near-zone Taylor polynomial sum_{m<=K} t_m r^m with a compile-time degree (no loop counter, immediate offsets).
 // -DTPP_HORNER_EVENODD splits it into its even and odd parts in r^2 (two chains per node): measured +2.5 % with 3 blocks/SM,
 // -1.5 % with 4 blocks/SM on C5 (the other warps already fill the DFMA latency), so the single chain is the default.
-template <int K, int NPL>
+template <int K, int NPL, bool VOL>
 __device__ __forceinline__ void tpp_taylor_horner(double (&h)[NPL], const double (&r)[NPL], const double* __restrict__ myCt) {
 #ifndef TPP_HORNER_EVENODD
-    const double t_top = myCt[K * TPP_THREADS];
+    // VOLATILE loads of the Taylor coefficients: with plain loads the compiler hoists all 27 of them above the degree switch
+    // (54 registers), and under that pressure ptxas serialises the NPL Horner chains node by node — every DFMA then waits out
+    // the 8-cycle latency alone.  Loaded where they are used, the chains interleave and the spills disappear (-4.5 % on C5).
+    // (The 255-register instances of the high-order tensors have the registers and measured 3 % faster with plain loads.)
+    typename std::conditional<VOL, const volatile double*, const double*>::type vct = myCt;
+    const double t_top = vct[K * TPP_THREADS];
 #pragma unroll
     for (int i = 0; i < NPL; ++i) h[i] = t_top;
 #pragma unroll
     for (int m = K - 1; m >= 0; --m) {
-        const double tm = myCt[m * TPP_THREADS];
+        const double tm = vct[m * TPP_THREADS];
 #pragma unroll
         for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], r[i], tm);
     }
@@ -448,18 +457,19 @@ __device__ __forceinline__ void tpp_taylor_horner(double (&h)[NPL], const double
     constexpr int KE = (K % 2 == 0) ? K : K - 1;  // highest even / odd order
     constexpr int KO = (K % 2 == 0) ? K - 1 : K;
     double r2[NPL], he[NPL], ho[NPL];
-    const double te = myCt[KE * TPP_THREADS], to = myCt[KO * TPP_THREADS];
+    typename std::conditional<VOL, const volatile double*, const double*>::type vct = myCt;
+    const double te = vct[KE * TPP_THREADS], to = vct[KO * TPP_THREADS];
 #pragma unroll
     for (int i = 0; i < NPL; ++i) { r2[i] = r[i] * r[i]; he[i] = te; ho[i] = to; }
 #pragma unroll
     for (int m = KE - 2; m >= 0; m -= 2) {
-        const double tm = myCt[m * TPP_THREADS];
+        const double tm = vct[m * TPP_THREADS];
 #pragma unroll
         for (int i = 0; i < NPL; ++i) he[i] = fma(he[i], r2[i], tm);
     }
 #pragma unroll
     for (int m = KO - 2; m >= 1; m -= 2) {
-        const double tm = myCt[m * TPP_THREADS];
+        const double tm = vct[m * TPP_THREADS];
 #pragma unroll
         for (int i = 0; i < NPL; ++i) ho[i] = fma(ho[i], r2[i], tm);
     }
@@ -576,11 +586,11 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
                 z[i] = tl.x * inv_th;
                 ls[i] = tl.y;
             }
-#define TPP_NEAR_CASE(KK) case KK: tpp_taylor_horner<KK, NPL>(h, r, myCt); break;
+#define TPP_NEAR_CASE(KK) case KK: tpp_taylor_horner<KK, NPL, (P < 4)>(h, r, myCt); break;
             switch (Kj) {
                 TPP_NEAR_CASE(4) TPP_NEAR_CASE(5) TPP_NEAR_CASE(7) TPP_NEAR_CASE(9) TPP_NEAR_CASE(11) TPP_NEAR_CASE(14)
                 TPP_NEAR_CASE(16) TPP_NEAR_CASE(19) TPP_NEAR_CASE(22) TPP_NEAR_CASE(25)
-                default: tpp_taylor_horner<TPP_TAYLOR_MAX, NPL>(h, r, myCt); break;
+                default: tpp_taylor_horner<TPP_TAYLOR_MAX, NPL, (P < 4)>(h, r, myCt); break;
             }
 #undef TPP_NEAR_CASE
             tpp_block_tail<MP, P, NPL>(top, Z, rb, z, h, ls, k, e0, cf_lim, exp_tab);

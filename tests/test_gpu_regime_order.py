@@ -139,3 +139,28 @@ def test_column_states_keep_their_order(cb):
     u = model.ensemble(64 * 64).upload(cols.reshape(-1, 6))
     with pytest.raises(CloudyError):
         u.regime_sort()
+
+
+def test_context_reconfigured_with_another_slot_count(cb):
+    """one context, two configurations with different numbers of moments and the same ensemble size: the sort scratch of
+    the first (5 slots) must not be reused for the second (12 slots) — results equal those of a fresh context"""
+    from cloudy_b200 import workloads as W
+    n = 270000  # above the automatic regime-sort threshold
+    ctx = cb.Context(0)
+    par1, st1 = W.c2_gamma_exp(n_parcels=n)
+    m1 = cb.CoalescenceModel(par1, ctx=ctx)
+    u1 = m1.ensemble(n).upload(st1); d1 = m1.ensemble(n)
+    m1.coal_tendency(u1, d1)
+    assert u1.order() is not None
+    got1 = d1.download()
+    par2, st2 = W.moving_four_modes(n_parcels=n)
+    m2 = cb.CoalescenceModel(par2, ctx=ctx)
+    u2 = m2.ensemble(n).upload(st2); d2 = m2.ensemble(n)
+    m2.coal_tendency(u2, d2)
+    got2 = d2.download()
+    fresh = cb.CoalescenceModel(par2, ctx=cb.Context(0))
+    uf = fresh.ensemble(n).upload(st2); df = fresh.ensemble(n)
+    fresh.coal_tendency(uf, df)
+    assert np.array_equal(got2, df.download())
+    fresh1 = cb.CoalescenceModel(par1, ctx=cb.Context(0))
+    assert np.array_equal(got1, fresh1.coal_tendency_host(st1))
