@@ -1743,9 +1743,21 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
                     tab3.push_back(r[REC_LSUM]);
                     for (int p = 0; p < S2 - 2; ++p) tab3.push_back((p <= P && !dummy) ? r[REC_W + p] : 0.0);
                 };
+                for (int c = 0; c < TPP_N_CLASSES; ++c) d.near_cls_end[i][c] = 0;
+                int prev_class = 0;
                 for (int q = 0; q < n_near; ++q) {
                     push2(r0 + (size_t)q * R, false);
-                    if ((q + 1) % tpp_npl(P) == 0) kblk3.push_back(r0[(size_t)q * R + REC_K]);
+                    if ((q + 1) % tpp_npl(P) == 0) {
+                        // degree of the block = degree of its last node, rounded up to its class (both near-zone loops of the
+                        // kernel use this value, so a parcel's result does not depend on the loop its warp runs)
+                        const int kq = (int)r0[(size_t)q * R + REC_K];
+                        int cls = 0;
+                        while (cls < TPP_N_CLASSES - 1 && tpp_taylor_class(cls) < kq) ++cls;
+                        if (cls < prev_class) return fail(CLOUDY_ERR_STATE, "internal: near-zone Taylor degrees are not sorted");
+                        prev_class = cls;
+                        kblk3.push_back((double)tpp_taylor_class(cls));
+                        for (int c = cls; c < TPP_N_CLASSES; ++c) d.near_cls_end[i][c] = (int)((q + 1) / tpp_npl(P));
+                    }
                 }
                 int n_far2 = 0;
                 for (int q = n_near; q < n_near + n_far; ++q) {

@@ -39,6 +39,7 @@ struct DevConfig {
     int tpp2_off, tpp2_total, gl2_off;
     int rec2_off[MAXN], kblk2_off[MAXN];  // per quadrature mode: records (tmx, lsum, w_0..w_P, pad) and Taylor degree per node block
     int rec2_far[MAXN];                   // far nodes padded to a multiple of TPP_NPLF, at least one zero-weight dummy at the end
+    int near_cls_end[MAXN][5];            // near blocks [0, end[c]) have a Taylor degree class <= c (classes kTaylorClass, tpp_kernel.cuh)
     int n_vel, nz;
     double c[MAXN][MAXN][MAXP][MAXP];
     double thr[MAXN];

@@ -46,7 +46,11 @@ constexpr int TPP_CT_ROWS = 64;  // MovingThreshold instances: series coefficien
 constexpr int TPP_CT_ROWS_FIXED = 27;
 constexpr int TPP_NPLF = 5;       // far-zone nodes in flight per thread (FixedThreshold): one coefficient product serves five Horner chains
 __host__ __device__ constexpr int tpp_ct_rows(int model) { return model == 2 /*MODEL_BOX_MOVING*/ ? TPP_CT_ROWS : TPP_CT_ROWS_FIXED; }
-constexpr int TPP_TAYLOR_MAX = 26;  // Taylor coefficients t_0..t_26 of the near-node expansion
+constexpr int TPP_TAYLOR_MAX = 26;
+// FixedThreshold near zone: the node-only Taylor degrees (4..26) are rounded up to five classes; the near blocks are sorted by
+// degree, so each class is a run of consecutive blocks and gets its own loop with a compile-time degree (no per-block dispatch)
+constexpr int TPP_N_CLASSES = 5;
+__host__ __device__ constexpr int tpp_taylor_class(int c) { return c == 0 ? 5 : c == 1 ? 7 : c == 2 ? 11 : c == 3 ? 16 : TPP_TAYLOR_MAX; }  // Taylor coefficients t_0..t_26 of the near-node expansion
 
 __host__ __device__ constexpr int tri_ct(int p1, int p2, int MP) { return p1 * MP - (p1 * (p1 - 1)) / 2 + (p2 - p1); }
 
@@ -492,7 +496,8 @@ __device__ __forceinline__ void tpp_taylor_horner(double (&h)[NPL], const double
 
 struct FixedGrid {
     const double* rec;    // shared memory: aligned records, [near | far]
-    const double* kblk;   // shared memory: Taylor degree per near block
+    const double* kblk;   // shared memory: Taylor degree per near block (rounded up to its class)
+    const int* cls_end;   // constant bank: near blocks [0, cls_end[c]) belong to the degree classes <= c
     int n_near, n_far;    // padded node counts
     // natural-order SoA tables in global memory (continued-fraction nodes only): XJ[nb] ELL[nb] TMX[nb] LZ[nb] W[M][nb]
     const double* soa;
@@ -587,26 +592,31 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
     const int n_near_b = grid.n_near / NPL;
     constexpr int CAP_UNROLL = (P >= 4) ? TPP_TAYLOR_MAX + 1 : 1;
     if (!warp_capped) {
-        for (int bt = 0; bt < n_near_b; ++bt) {
-            const double2* __restrict__ rb = reinterpret_cast<const double2*>(grid.rec + bt * NPL * S2);
-            const int Kj = (int)grid.kblk[bt];  // node-only degree: the same for every parcel
-            double z[NPL], h[NPL], ls[NPL], r[NPL];
+        // one loop per degree class: loop bounds are run constants (uniform registers), the degree is a compile-time constant of
+        // the loop body — the per-block jump table of the earlier version (LDS + F2I + LDC + BRX on the critical path of
+        // every block) cost 6-8 % of the kernel
+        int bt = 0;
+        auto run_class = [&](auto ktag, const int end) {
+            constexpr int K = decltype(ktag)::value;
+            for (; bt < end; ++bt) {
+                const double2* __restrict__ rb = reinterpret_cast<const double2*>(grid.rec + bt * NPL * S2);
+                double z[NPL], h[NPL], ls[NPL], r[NPL];
 #pragma unroll
-            for (int i = 0; i < NPL; ++i) {
-                const double2 tl = rb[i * (S2 / 2)];
-                r[i] = fma(tl.x, rq, -1.0);
-                z[i] = tl.x * inv_th;
-                ls[i] = tl.y;
+                for (int i = 0; i < NPL; ++i) {
+                    const double2 tl = rb[i * (S2 / 2)];
+                    r[i] = fma(tl.x, rq, -1.0);
+                    z[i] = tl.x * inv_th;
+                    ls[i] = tl.y;
+                }
+                tpp_taylor_horner<K, NPL, (P < 4)>(h, r, myCt);
+                tpp_block_tail<MP, P, NPL>(top, Z, rb, z, h, ls, k, e0, cf_lim, exp_tab);
             }
-#define TPP_NEAR_CASE(KK) case KK: tpp_taylor_horner<KK, NPL, (P < 4)>(h, r, myCt); break;
-            switch (Kj) {
-                TPP_NEAR_CASE(4) TPP_NEAR_CASE(5) TPP_NEAR_CASE(7) TPP_NEAR_CASE(9) TPP_NEAR_CASE(11) TPP_NEAR_CASE(14)
-                TPP_NEAR_CASE(16) TPP_NEAR_CASE(19) TPP_NEAR_CASE(22) TPP_NEAR_CASE(25)
-                default: tpp_taylor_horner<TPP_TAYLOR_MAX, NPL, (P < 4)>(h, r, myCt); break;
-            }
-#undef TPP_NEAR_CASE
-            tpp_block_tail<MP, P, NPL>(top, Z, rb, z, h, ls, k, e0, cf_lim, exp_tab);
-        }
+        };
+        run_class(std::integral_constant<int, tpp_taylor_class(0)>{}, grid.cls_end[0]);
+        run_class(std::integral_constant<int, tpp_taylor_class(1)>{}, grid.cls_end[1]);
+        run_class(std::integral_constant<int, tpp_taylor_class(2)>{}, grid.cls_end[2]);
+        run_class(std::integral_constant<int, tpp_taylor_class(3)>{}, grid.cls_end[3]);
+        run_class(std::integral_constant<int, tpp_taylor_class(4)>{}, n_near_b);
     } else {
         for (int bt = 0; bt < n_near_b; ++bt) {
             const double2* __restrict__ rb = reinterpret_cast<const double2*>(grid.rec + bt * NPL * S2);
@@ -1136,6 +1146,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                                 FixedGrid fg;
                                 fg.rec = sTab + cfg.rec2_off[i];
                                 fg.kblk = sTab + cfg.kblk2_off[i];
+                                fg.cls_end = cfg.near_cls_end[i];
                                 fg.n_near = cfg.rec_near[i];
                                 fg.n_far = cfg.rec2_far[i];
                                 fg.soa = cfg.tab + cfg.tab_off[i];
