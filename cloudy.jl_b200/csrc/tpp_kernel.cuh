@@ -450,11 +450,9 @@ __device__ __forceinline__ void tpp_block_tail(double (&top)[P + 1], double (&Z)
 }
 
 // Near-zone Taylor polynomial sum_{m<=K} t_m r^m with a compile-time degree (no loop counter, immediate offsets).
-// -DTPP_HORNER_EVENODD splits it into its even and odd parts in r^2 (two chains per node): measured +2.5 % with 3 blocks/SM,
-// -1.5 % with 4 blocks/SM on C5 (the other warps already fill the DFMA latency), so the single chain is the default.
+// (Splitting it into its even and odd parts in r^2, two chains per node, was measured: +2.5 % with 3 blocks/SM, -1.5 % with 4.)
 template <int K, int NPL, bool VOL>
 __device__ __forceinline__ void tpp_taylor_horner(double (&h)[NPL], const double (&r)[NPL], const double* __restrict__ myCt) {
-#ifndef TPP_HORNER_EVENODD
     // VOLATILE loads of the Taylor coefficients: with plain loads the compiler hoists all 27 of them above the degree switch
     // (54 registers), and under that pressure ptxas serialises the NPL Horner chains node by node — every DFMA then waits out
     // the 8-cycle latency alone.  Loaded where they are used, the chains interleave and the spills disappear (-4.5 % on C5).
@@ -469,29 +467,6 @@ __device__ __forceinline__ void tpp_taylor_horner(double (&h)[NPL], const double
 #pragma unroll
         for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], r[i], tm);
     }
-#else
-    constexpr int KE = (K % 2 == 0) ? K : K - 1;  // highest even / odd order
-    constexpr int KO = (K % 2 == 0) ? K - 1 : K;
-    double r2[NPL], he[NPL], ho[NPL];
-    typename std::conditional<VOL, const volatile double*, const double*>::type vct = myCt;
-    const double te = vct[KE * TPP_THREADS], to = vct[KO * TPP_THREADS];
-#pragma unroll
-    for (int i = 0; i < NPL; ++i) { r2[i] = r[i] * r[i]; he[i] = te; ho[i] = to; }
-#pragma unroll
-    for (int m = KE - 2; m >= 0; m -= 2) {
-        const double tm = vct[m * TPP_THREADS];
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) he[i] = fma(he[i], r2[i], tm);
-    }
-#pragma unroll
-    for (int m = KO - 2; m >= 1; m -= 2) {
-        const double tm = vct[m * TPP_THREADS];
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) ho[i] = fma(ho[i], r2[i], tm);
-    }
-#pragma unroll
-    for (int i = 0; i < NPL; ++i) h[i] = fma(ho[i], r[i], he[i]);
-#endif
 }
 
 struct FixedGrid {
@@ -840,21 +815,11 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
         const long long q = (ix < n) ? ix : n - 1;
         return (args.perm != nullptr) ? (long long)args.perm[q] : q;
     };
-#ifdef TPP_PREFETCH_REGS
-    double nxt[N][3];
-#endif
     long long p_next = 0;
     {
         const long long b0 = blockIdx.x * (long long)TPP_THREADS + (tid & ~31);
         if (b0 < n) {
             p_next = parcel_of(b0);
-#ifdef TPP_PREFETCH_REGS
-#pragma unroll
-            for (int i = 0; i < N; ++i)
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-                    nxt[i][q] = (q < cfg.nprog[i]) ? args.u_in[(cfg.slot0[i] + q) * args.s_in + p_next * args.ps_in] : 0.0;
-#endif
         }
     }
     for (long long base = blockIdx.x * (long long)TPP_THREADS + (tid & ~31); base < n; base += stride_all) {
@@ -862,20 +827,6 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
         const bool live = idx < n;
         const long long p = p_next;
         double cur[N][3];
-#ifdef TPP_PREFETCH_REGS
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-#pragma unroll
-            for (int q = 0; q < 3; ++q) cur[i][q] = nxt[i][q];
-        if (base + stride_all < n) {
-            p_next = parcel_of(base + stride_all);
-#pragma unroll
-            for (int i = 0; i < N; ++i)
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-                    nxt[i][q] = (q < cfg.nprog[i]) ? args.u_in[(cfg.slot0[i] + q) * args.s_in + p_next * args.ps_in] : 0.0;
-        }
-#else
         // this parcel's moments (requested one iteration ago with an L2 prefetch: holding the NEXT parcel's values in registers
         // across the node loops made the 128-register instances spill them, and the spill store waits for the DRAM load)
 #pragma unroll
@@ -892,7 +843,6 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                     if (q < cfg.nprog[i])
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(args.u_in + (cfg.slot0[i] + q) * args.s_in + p_next * args.ps_in));
         }
-#endif
         // zero flux above the column top (rainshaft_helpers.jl:80-81); one 64-bit modulo per cell
         const bool top_level = RAIN && ((p + 1) % cfg.nz == 0);
         if constexpr (RAIN) {
