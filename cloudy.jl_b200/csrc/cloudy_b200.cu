@@ -713,20 +713,24 @@ __global__ void scalar_kernel(const ScalarArgs a) {
 
 // sedimentation flux of every cell, thread per cell — Sedimentation.jl:22-37 with the velocity normalisation of
 // rainshaft_helpers.jl:74-77.  moment(dist, q+β) for q = 0,1,2 follows from the q = 0 value by Γ(x+1) = xΓ(x).
-__global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevConfig cfg, const KArgs args) {
+// One instance per mode count (every loop over modes unrolls with no `i < cfg.N` test, half the registers of a MAXN body:
+// 29.7 M -> see profiles/ for the instruction count per Mi cells); a warp whose cells are all empty writes zeros at once.
+template <int NM>
+__global__ void __launch_bounds__(256, 4) flux_kernel(const __grid_constant__ DevConfig cfg, const KArgs args) {
+    const double* __restrict__ uin = args.u_in;
+    double* __restrict__ out = args.out;
     for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < args.n; p += (long long)gridDim.x * blockDim.x) {
         // every moment of the cell is requested before any arithmetic: the kernel is load-latency bound otherwise
-        double raw[MAXN][3];
+        double raw[NM][3];
 #pragma unroll
-        for (int i = 0; i < MAXN; ++i)
+        for (int i = 0; i < NM; ++i)
 #pragma unroll
             for (int q = 0; q < 3; ++q)
-                raw[i][q] = (i < cfg.N && q < cfg.nprog[i]) ? __ldg(args.u_in + (cfg.slot0[i] + q) * args.s_in + p * args.ps_in) : 0.0;
-        double pn[MAXN], pa[MAXN], pb[MAXN];
+                raw[i][q] = (q < cfg.nprog[i]) ? __ldg(uin + (cfg.slot0[i] + q) * args.s_in + p * args.ps_in) : 0.0;
+        double pn[NM], pa[NM], pb[NM];
 #pragma unroll
-        for (int i = 0; i < MAXN; ++i) {
+        for (int i = 0; i < NM; ++i) {
             pn[i] = 0.0; pa[i] = 1.0; pb[i] = 1.0;
-            if (i >= cfg.N) continue;
             // a mode without number or mass (most cells of a column: exact zeros, or clipped negatives) is the empty-mode fallback of
             // update_dist_from_moments (n = 0) whatever the normalisation: no divisions, no flux
             if (!(raw[i][0] > 0.0) || !(raw[i][1] > 0.0)) continue;
@@ -743,14 +747,13 @@ __global__ void __launch_bounds__(256) flux_kernel(const __grid_constant__ DevCo
                                                       kind == CLOUDY_GAMMA ? cfg.k_hi : INFINITY);
             pn[i] = mp.n; pa[i] = mp.a; pb[i] = mp.b;
         }
-        double fl[MAXN][3];
-        cell_flux<MAXN>(cfg, pn, pa, pb, fl);
+        double fl[NM][3];
+        cell_flux<NM>(cfg, pn, pa, pb, fl);
 #pragma unroll
-        for (int i = 0; i < MAXN; ++i) {
-            if (i >= cfg.N) continue;
+        for (int i = 0; i < NM; ++i) {
 #pragma unroll
             for (int q = 0; q < 3; ++q)
-                if (q < cfg.nprog[i]) args.out[(cfg.slot0[i] + q) * args.s_out + p * args.ps_out] = fl[i][q];
+                if (q < cfg.nprog[i]) out[(cfg.slot0[i] + q) * args.s_out + p * args.ps_out] = fl[i][q];
         }
     }
 }
@@ -1200,9 +1203,18 @@ static int ensure_flux(cloudy_ctx* ctx, long long n);
 }
 
 static int launch_flux(cloudy_ctx* ctx, const KArgs& args) {
-    long long blocks = std::min<long long>((args.n + 255) / 256, (long long)ctx->sm_count * 8);
+    int per_sm = 8;
+    if (const char* e = getenv("CLOUDY_FLUX_BLOCKS")) per_sm = std::max(1, atoi(e));
+    long long blocks = std::min<long long>((args.n + 255) / 256, (long long)ctx->sm_count * per_sm);
     void* params[2] = {(void*)&ctx->dev, (void*)&args};
-    CUDA_TRY(cudaLaunchKernel((const void*)flux_kernel, dim3((unsigned)std::max<long long>(blocks, 1)), dim3(256), params, 0, ctx->stream));
+    const void* fn = nullptr;
+    switch (ctx->dev.N) {
+        case 1: fn = (const void*)flux_kernel<1>; break;
+        case 2: fn = (const void*)flux_kernel<2>; break;
+        case 3: fn = (const void*)flux_kernel<3>; break;
+        default: fn = (const void*)flux_kernel<MAXN>; break;
+    }
+    CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)std::max<long long>(blocks, 1)), dim3(256), params, 0, ctx->stream));
     ctx->launches++;
     return CLOUDY_OK;
 }
@@ -1630,6 +1642,22 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
                     if (cfg->c[j][k][a][b] != cfg->c[j][k][b][a]) return fail(CLOUDY_ERR_ARG, "array not symmetric.");
                     d.c[j][k][a][b] = cfg->c[j][k][a][b];
                 }
+    // S terms of the thread-per-parcel kernel: sw[k][m][t(u,v)] = sum over (a, b, c) with {a+c, b+m-c} = {u, v} of
+    // 0.5 c^{kk}_ab binomial(m, c) (Coalescence.jl:353-455 with F symmetric) — one multiply-add per (m, u <= v) in the kernel
+    memset(d.sw, 0, sizeof(d.sw));
+    {
+        const int M = P + 2;
+        for (int k = 0; k < N; ++k)
+            for (int m = 0; m < 3; ++m)
+                for (int a = 0; a < P; ++a)
+                    for (int b = 0; b < P; ++b)
+                        for (int c = 0; c <= m; ++c) {
+                            const int x = a + c, y = b + m - c;
+                            const int u = std::min(x, y), v = std::max(x, y);
+                            const double binom = (m == 2 && c == 1) ? 2.0 : 1.0;
+                            d.sw[k][m][u * M - (u * (u - 1)) / 2 + (v - u)] += 0.5 * cfg->c[k][k][a][b] * binom;
+                        }
+    }
     // grid tables
     std::vector<double> tab, tab2;  // tab: SoA tables of the lane-cooperative kernel; tab2: records / rules of the thread-per-parcel kernel
     std::vector<double> tab3, kblk3;  // FixedThreshold thread-per-parcel kernels: aligned records, Taylor degree per node block
@@ -2115,6 +2143,7 @@ int cloudy_ssprk33_steps(cloudy_ctx* ctx, cloudy_state* u, double dt, int32_t n_
         // stage 1: tmp = u + dt f(u)
         a.u_in = cur; a.u_n = nullptr; a.out = t1; a.cn = 0; a.ci = 1; a.cf = 1; a.div = 1;
         ctx->perm_valid = false;  // column model: new permutation sort (if enabled) at the first stage, reused by stages 2 and 3
+        // (reusing it across steps was measured: 1.27 -> 1.42 ms per C3 step, sedimentation moves the cloud edge every step)
         ctx->perm_fresh = false;
         if ((rc = launch_rhs(ctx, model, a))) return rc;
         ctx->perm_valid = ctx->perm_fresh;

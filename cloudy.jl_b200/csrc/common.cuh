@@ -42,6 +42,7 @@ struct DevConfig {
     int near_cls_end[MAXN][5];            // near blocks [0, end[c]) have a Taylor degree class <= c (classes kTaylorClass, tpp_kernel.cuh)
     int n_vel, nz;
     double c[MAXN][MAXN][MAXP][MAXP];
+    double sw[MAXN][3][MAXT];      // folded S-term weights by (mode, order m, t(u,v) of the M x M triangle), see cloudy_config_set
     double thr[MAXN];
     double norm[MAXSLOT];
     double k_lo, k_hi;

@@ -734,35 +734,33 @@ __device__ __noinline__ void tpp_lognormal_H(double (&acc)[MP * (MP + 1) / 2], c
     }
 }
 
-// S_1k and S_2k of one mode, all orders m < 3 — Coalescence.jl:353-455.  F(x,y) is supplied by a functor.
-template <int P, typename FGet>
-__device__ __forceinline__ void tpp_s_terms(const DevConfig& cfg, const int k, const double (&momk)[P + 2], FGet F, double (&s1)[3], double (&s2)[3]) {
+// S_1k and S_2k of one mode, all orders m < 3 — Coalescence.jl:353-455.  The reference sums 0.5 c_ab binomial(m,c) F(a+c, b+m-c)
+// over (a, b, c); F is symmetric, so the sum is folded on the host into one weight per (m, u <= v) (DevConfig::sw): one
+// multiply-add per weight here instead of P*P*(m+1) terms with their index arithmetic — for P = 5 the three unrolled copies per
+// mode were 15 k of the kernel's 26 k instructions.  Fs[t(u,v)] holds the truncated integrals (already limited and masked),
+// S2 uses Mom_u Mom_v - F in the same weights.
+template <int P>
+__device__ __forceinline__ void tpp_s_terms(const DevConfig& cfg, const int k, const double (&momk)[P + 2],
+                                            const double (&Fs)[(P + 2) * (P + 3) / 2], double (&s1)[3], double (&s2)[3]) {
+    constexpr int M = P + 2;
+    double a1[3] = {0.0, 0.0, 0.0}, a2[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-    for (int m = 0; m < 3; ++m) {
-        double a1 = 0.0, a2 = 0.0;
+    for (int u = 0; u < M; ++u)
 #pragma unroll
-        for (int a = 0; a < P; ++a) {
-            double b1 = 0.0, b2 = 0.0;
+        for (int v = u; v < M; ++v) {
+            if (u + v > 2 * P) continue;  // a + b + m <= 2P: never referenced
+            const int t = tri_ct(u, v, M);
+            const double f = Fs[t];
+            const double d = momk[u] * momk[v] - f;
 #pragma unroll
-            for (int b = 0; b < P; ++b) {
-                const double hc = 0.5 * cfg.c[k][k][a][b];
-                double c1 = 0.0, c2 = 0.0;
-#pragma unroll
-                for (int c = 0; c <= m; ++c) {
-                    const double h = (m == 2 && c == 1) ? hc * 2.0 : hc;  // 0.5 * c_ab * binomial(m, c)
-                    const double f = F(a + c, b + m - c);
-                    c1 = fma(h, f, c1);
-                    c2 = fma(h, momk[a + c] * momk[b + m - c] - f, c2);
-                }
-                b1 += c1;
-                b2 += c2;
+            for (int m = 0; m < 3; ++m) {
+                if (u + v < m || u + v > 2 * (P - 1) + m) continue;  // a + b = u + v - m must lie in [0, 2(P-1)]
+                a1[m] = fma(cfg.sw[k][m][t], f, a1[m]);
+                a2[m] = fma(cfg.sw[k][m][t], d, a2[m]);
             }
-            a1 += b1;
-            a2 += b2;
         }
-        s1[m] = a1;
-        s2[m] = a2;
-    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { s1[m] = a1[m]; s2[m] = a2[m]; }
 }
 
 struct TppShared {
@@ -923,6 +921,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             double s1[3], s2[3];
+            double Fs[M * (M + 1) / 2];  // this mode's truncated integrals F(u, v), u <= v
             const int n2d = cfg.n2d[i];
             bool done = false;
             if (i < N - 1 && (cfg.quad[i] || cfg.ln_thr[i])) {
@@ -930,10 +929,11 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                 const bool skip = (nmd == 0.0) || cell_empty || !live;
                 if (!__all_sync(0xffffffffu, skip)) {
                     const int Mp = cfg.Mp[i];
-                    // contraction of the truncated integrals H (raw quadrature sums scaled by `scale[p2]`) into S1, S2
+                    // the truncated integrals H (raw quadrature sums scaled by `scale[p2]`), limited and masked, into Fs
                     auto contract = [&](auto mp_tag, auto& F, const double* scale) {
                         constexpr int MP = decltype(mp_tag)::value;
-                        // F = 0 | min(Mom*Mom, H) — Coalescence.jl:212-227
+                        static_assert(MP == M, "all M = P + 2 orders are carried");
+                        // F = 0 | min(Mom*Mom, H) — Coalescence.jl:212-227; zero beyond N_2d_ints (Coalescence.jl:213)
 #pragma unroll
                         for (int p1 = 0; p1 < MP; ++p1)
 #pragma unroll
@@ -941,12 +941,8 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                                 const int t = tri_ct(p1, p2, MP);
                                 const double mm = mom[i][p1] * mom[i][p2];
                                 const double H = scale[p2] * F[t];
-                                F[t] = (mm < kEps) ? 0.0 : jl_min(mm, H);
+                                Fs[t] = (mm < kEps || p2 >= Mp) ? 0.0 : jl_min(mm, H);
                             }
-                        tpp_s_terms<P>(cfg, i, mom[i], [&](int x, int y) -> double {
-                            if (x >= Mp || y >= Mp) return 0.0;  // beyond N_2d_ints (Coalescence.jl:213)
-                            return (x <= y) ? F[tri_ct(x < MP ? x : 0, y < MP ? y : 0, MP)] : F[tri_ct(y < MP ? y : 0, x < MP ? x : 0, MP)];
-                        }, s1, s2);
                     };
                     if (cfg.ln_thr[i]) {
                         // Lognormal: (n, μ, σ) = (nmd, th, k)
@@ -1119,20 +1115,23 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                 const bool quad_skipped = (i < N - 1) && (cfg.quad[i] || cfg.ln_thr[i]);  // whole warp empty: F = 0
                 const double th = pa[i], nn = pn[i];
                 const bool below = th < cfg.thr[i] / 2;
-                tpp_s_terms<P>(cfg, i, mom[i], [&](int x, int y) -> double {
-                    const double mm = mom[i][x] * mom[i][y];
-                    if (mm < kEps || x >= n2d || y >= n2d || quad_skipped) return 0.0;
-                    if (mono) {  // ParticleDistributions.jl:557-564
-                        double h = 0.0;
-                        if (below) {
-                            h = nn * nn;
-                            for (int e = 0; e < x + y; ++e) h *= th;
-                        }
-                        return jl_min(mm, h);
+                double hpow[2 * P + 1];  // Monodisperse: n^2 θ^(u+v) below the threshold (ParticleDistributions.jl:557-564)
+                hpow[0] = nn * nn;
+#pragma unroll
+                for (int e = 1; e <= 2 * P; ++e) hpow[e] = hpow[e - 1] * th;
+#pragma unroll
+                for (int x = 0; x < M; ++x)
+#pragma unroll
+                    for (int y = x; y < M; ++y) {
+                        if (x + y > 2 * P) continue;
+                        const double mm = mom[i][x] * mom[i][y];
+                        double f = mm;  // last mode or infinite threshold
+                        if (mono) f = jl_min(mm, below ? hpow[x + y] : 0.0);
+                        if (mm < kEps || y >= n2d || quad_skipped) f = 0.0;
+                        Fs[tri_ct(x, y, M)] = f;
                     }
-                    return mm;  // last mode or infinite threshold
-                }, s1, s2);
             }
+            tpp_s_terms<P>(cfg, i, mom[i], Fs, s1, s2);
 #pragma unroll
             for (int m = 0; m < 3; ++m) {
                 res[i][m] += s1[m];
