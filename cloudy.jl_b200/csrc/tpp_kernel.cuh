@@ -860,16 +860,15 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
 
         // ---- load, (clip), normalise, parameters, moment matrix --------------------------------------
         double raw[N][3];
-        double mom[N][M];
-        double pn[N], pa[N], pb[N];
+        double mnv[N][3];  // normalised moments
         bool cell_empty = RAIN;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const int s0 = cfg.slot0[i], np = cfg.nprog[i], kind = cfg.kind[i];
-            double mn[3] = {0.0, 0.0, 0.0};
+            const int s0 = cfg.slot0[i], np = cfg.nprog[i];
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 raw[i][q] = 0.0;
+                mnv[i][q] = 0.0;
                 if (q < np) {
                     double v = cur[i][q];
                     if (RAIN) {
@@ -877,15 +876,90 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                         if (args.clip_back != nullptr && live) args.clip_back[(s0 + q) * args.s_clip + p] = v;
                     }
                     raw[i][q] = v;
-                    mn[q] = v / cfg.norm[s0 + q];
-                    if (RAIN) cell_empty = cell_empty && (mn[q] < kEps);  // rainshaft_helpers.jl:67
+                    // a zero dividend always takes the ~100-instruction slow path of the FP64 division (13 % of the rainshaft
+                    // instance's executed instructions: 61 % of the C3 cells are exact zeros); 0/norm = 0 with v's sign
+                    mnv[i][q] = (v == 0.0) ? v : v / cfg.norm[s0 + q];
+                    if (RAIN) cell_empty = cell_empty && (mnv[i][q] < kEps);  // rainshaft_helpers.jl:67
                 }
             }
+        }
+
+        double res[N][3];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) res[i][q] = 0.0;
+
+        // rainshaft: a warp whose cells are all empty (rainshaft_helpers.jl:67-68) has zero coalescence source: it skips the
+        // distribution parameters, the moment matrix and the whole contraction (with the regime sort empty cells share warps;
+        // 61 % of the C3 cells are empty) and goes straight to the flux divergence and the stage update
+        const bool warp_idle = RAIN && __all_sync(0xffffffffu, cell_empty || !live);
+        if constexpr (RAIN) {
+            if (warp_idle) {
+                // Compact path of the empty warps: flux divergence + stage update (all loads first), next to the
+                // top of the parcel loop, so that the 61 % of warps that never enter the contraction run from a few KB of code
+                // instead of jumping across the kernel's 130 KB (instruction fetch was 29 % of this instance's stall samples).
+                // Same expressions, in the same order, as the general epilogue below with f_coal = 0.
+                if (live) {
+                    const double inv_dz_c = 1.0 / cfg.dz;
+                    const bool with_un = !args.tend_only && args.u_n != nullptr;
+                    double unc[N][3], flc[N][3], fuc[N][3];
+#pragma unroll
+                    for (int k = 0; k < N; ++k)
+#pragma unroll
+                        for (int m = 0; m < 3; ++m) {
+                            unc[k][m] = 0.0; flc[k][m] = 0.0; fuc[k][m] = 0.0;
+                            if (m < cfg.nprog[k]) {
+                                const int s = cfg.slot0[k] + m;
+                                flc[k][m] = args.flux[s * args.s_flux + p];
+                                if (!top_level) fuc[k][m] = args.flux[s * args.s_flux + p + 1];
+                                if (with_un) unc[k][m] = args.u_n[s * args.s_n + p];
+                            }
+                        }
+#pragma unroll
+                    for (int k = 0; k < N; ++k)
+#pragma unroll
+                        for (int m = 0; m < 3; ++m)
+                            if (m < cfg.nprog[k]) {
+                                const int s = cfg.slot0[k] + m;
+                                const double f = 0.0 + (-(fuc[k][m] - flc[k][m]) * inv_dz_c);
+                                double o;
+                                if (args.tend_only) {
+                                    o = f;
+                                } else {
+                                    double acc2 = args.ci * raw[k][m];
+                                    if (args.u_n != nullptr) {
+                                        double un = unc[k][m];
+                                        un = (un < 0.0) ? 0.0 : un;
+                                        acc2 = args.cn * un + acc2;
+                                    }
+                                    const double num = acc2 + args.cf * (args.dt * f);
+                                    o = (num == 0.0) ? num : div_rn_outofline(num, args.div);  // zero dividend: see the normalisation above
+                                    o = (o < 0.0) ? 0.0 : o;
+                                }
+                                args.out[s * args.s_out + p * args.ps_out] = o;
+                            }
+                }
+                continue;
+            }
+        }
+        double sumQ[N][3], sumR[N][3];
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+#pragma unroll
+            for (int m = 0; m < 3; ++m) { sumQ[k][m] = 0.0; sumR[k][m] = 0.0; }
+        if (!warp_idle) {
+        // ---- parameters, moment matrix ------------------------------------------------------------------
+        double mom[N][M];
+        double pn[N], pa[N], pb[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int np = cfg.nprog[i], kind = cfg.kind[i];
             ModeParams mp;
             if (args.params_in) {
                 mp.n = raw[i][0]; mp.a = raw[i][1]; mp.b = (np > 2) ? raw[i][2] : 1.0; mp.invalid = 0;
             } else {
-                mp = params_from_moments(kind, mn[0], mn[1], mn[2], kind == CLOUDY_GAMMA ? cfg.k_lo : -INFINITY,
+                mp = params_from_moments(kind, mnv[i][0], mnv[i][1], mnv[i][2], kind == CLOUDY_GAMMA ? cfg.k_lo : -INFINITY,
                                          kind == CLOUDY_GAMMA ? cfg.k_hi : INFINITY);
             }
             if (mp.invalid && live && args.err_count != nullptr) atomicAdd(args.err_count, 1ULL);
@@ -901,22 +975,6 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                 else mq *= mp.a;
             }
         }
-
-        double res[N][3];
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-#pragma unroll
-            for (int q = 0; q < 3; ++q) res[i][q] = 0.0;
-
-        // rainshaft: a warp whose cells are all empty (rainshaft_helpers.jl:67-68) has zero coalescence source: skip the
-        // whole contraction (with the regime sort empty cells share warps)
-        const bool warp_idle = RAIN && __all_sync(0xffffffffu, cell_empty || !live);
-        double sumQ[N][3], sumR[N][3];
-#pragma unroll
-        for (int k = 0; k < N; ++k)
-#pragma unroll
-            for (int m = 0; m < 3; ++m) { sumQ[k][m] = 0.0; sumR[k][m] = 0.0; }
-        if (!warp_idle) {
         // ---- S terms (self-collisions): truncated integrals of every mode, contracted at once ----------
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -1182,7 +1240,29 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
         }  // !warp_idle
 
         // ---- assemble, combine with the stage update, store ---------------------------------------------
+        // every global load of the epilogue (u^n, the two flux values per slot) is issued before the first use: the out-of-line
+        // division is a scheduling barrier, and one exposed L2 round trip per slot was 10 % of the rainshaft instance's samples
         const double inv_dz = 1.0 / cfg.dz;
+        double unv[N][3], flv[N][3], fluv[N][3];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const int s0 = cfg.slot0[k], np = cfg.nprog[k];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                unv[k][m] = 0.0; flv[k][m] = 0.0; fluv[k][m] = 0.0;
+                if (m < np && live) {
+                    const int s = s0 + m;
+                    if (!args.tend_only && args.u_n != nullptr) unv[k][m] = args.u_n[s * args.s_n + p];
+                    if (RAIN) {
+                        // flux of this cell and of the cell above it, written by flux_kernel.  (Evaluating both inside this kernel was
+                        // measured: 0.52 ms instead of 0.42 ms per RHS on C3 — the regime-sorted order separates vertical neighbours,
+                        // so every flux would be computed twice, ~1000 instructions each.)
+                        flv[k][m] = args.flux[s * args.s_flux + p];
+                        fluv[k][m] = top_level ? 0.0 : args.flux[s * args.s_flux + p + 1];
+                    }
+                }
+            }
+        }
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             const int s0 = cfg.slot0[k], np = cfg.nprog[k];
@@ -1195,12 +1275,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                     if (!args.params_in) f *= cfg.norm[s];
                     if (RAIN) {
                         if (cell_empty) f = 0.0;
-                        // flux of this cell and of the cell above it, written by flux_kernel.  (Evaluating both inside this kernel was
-                        // measured: 0.52 ms instead of 0.42 ms per RHS on C3 — the regime-sorted order separates vertical neighbours,
-                        // so every flux would be computed twice, ~1000 instructions each.)
-                        const double fl = args.flux[s * args.s_flux + p];
-                        const double fl_up = top_level ? 0.0 : args.flux[s * args.s_flux + p + 1];
-                        f = f + (-(fl_up - fl) * inv_dz);  // rainshaft_helpers.jl:83-87
+                        f = f + (-(fluv[k][m] - flv[k][m]) * inv_dz);  // rainshaft_helpers.jl:83-87
                     }
                     double o;
                     if (args.tend_only) {
@@ -1208,11 +1283,12 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                     } else {
                         double acc2 = args.ci * raw[k][m];
                         if (args.u_n != nullptr) {
-                            double un = args.u_n[s * args.s_n + p];
+                            double un = unv[k][m];
                             if (RAIN) un = (un < 0.0) ? 0.0 : un;
                             acc2 = args.cn * un + acc2;
                         }
-                        o = div_rn_outofline(acc2 + args.cf * (args.dt * f), args.div);
+                        const double num = acc2 + args.cf * (args.dt * f);
+                        o = (num == 0.0) ? num : div_rn_outofline(num, args.div);  // zero dividend: see the normalisation above
                         if (RAIN) o = (o < 0.0) ? 0.0 : o;
                     }
                     args.out[s * args.s_out + p * args.ps_out] = o;
