@@ -1232,6 +1232,14 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
         args.flux = ctx->flux->d;
         args.s_flux = ctx->flux->stride;
     }
+    {
+        // the kernel forms element offsets in 32 bits (tpp_kernel.cuh)
+        const long long smax = std::max({args.s_in, args.s_out, args.s_n, args.s_flux, args.s_clip});
+        const long long pmax = std::max<long long>({args.ps_in, args.ps_out, 1});
+        const unsigned long long span = (unsigned long long)smax * (unsigned long long)d.nslots + (unsigned long long)args.n * (unsigned long long)pmax;
+        if (span >= (1ULL << 32))
+            return fail(CLOUDY_ERR_UNSUPPORTED, "ensemble buffers of 2^32 doubles or more per device are not supported: split the ensemble");
+    }
     bool any_quad = false;
     for (int i = 0; i < d.N - 1; ++i) any_quad = any_quad || d.quad[i];
     const bool want_sort = ctx->sort_mode == 1 || (ctx->sort_mode == 2 && args.n >= 262144);  // auto: pays from ~2e5 parcels (measured)

@@ -807,13 +807,17 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
 
     const long long n = args.n;
     const long long stride_all = (long long)gridDim.x * TPP_THREADS;
+    // Element offsets are 32-bit unsigned (the host refuses buffers of 2^32 doubles or more, 34 GB each): one IMAD + one
+    // IMAD.WIDE per address instead of two 64-bit multiplies (~12 instructions) for each of the ~25 addresses of a parcel
+    const unsigned s_in = (unsigned)args.s_in, ps_in = (unsigned)args.ps_in, s_out = (unsigned)args.s_out, ps_out = (unsigned)args.ps_out;
+    const unsigned s_n = (unsigned)args.s_n, s_flux = (unsigned)args.s_flux, s_clip = (unsigned)args.s_clip;
     // software prefetch: the next parcel's moments are requested while the current one is being evaluated
-    auto parcel_of = [&](long long b) -> long long {
+    auto parcel_of = [&](long long b) -> unsigned {
         const long long ix = b + (tid & 31);
-        const long long q = (ix < n) ? ix : n - 1;
-        return (args.perm != nullptr) ? (long long)args.perm[q] : q;
+        const unsigned q = (unsigned)((ix < n) ? ix : n - 1);
+        return (args.perm != nullptr) ? (unsigned)args.perm[q] : q;
     };
-    long long p_next = 0;
+    unsigned p_next = 0;
     {
         const long long b0 = blockIdx.x * (long long)TPP_THREADS + (tid & ~31);
         if (b0 < n) {
@@ -823,7 +827,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
     for (long long base = blockIdx.x * (long long)TPP_THREADS + (tid & ~31); base < n; base += stride_all) {
         const long long idx = base + (tid & 31);
         const bool live = idx < n;
-        const long long p = p_next;
+        const unsigned p = p_next;
         double cur[N][3];
         // this parcel's moments (requested one iteration ago with an L2 prefetch: holding the NEXT parcel's values in registers
         // across the node loops made the 128-register instances spill them, and the spill store waits for the DRAM load)
@@ -831,7 +835,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
         for (int i = 0; i < N; ++i)
 #pragma unroll
             for (int q = 0; q < 3; ++q)
-                cur[i][q] = (q < cfg.nprog[i]) ? args.u_in[(cfg.slot0[i] + q) * args.s_in + p * args.ps_in] : 0.0;
+                cur[i][q] = (q < cfg.nprog[i]) ? args.u_in[(unsigned)(cfg.slot0[i] + q) * s_in + p * ps_in] : 0.0;
         if (base + stride_all < n) {
             p_next = parcel_of(base + stride_all);
 #pragma unroll
@@ -839,10 +843,10 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
                     if (q < cfg.nprog[i])
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(args.u_in + (cfg.slot0[i] + q) * args.s_in + p_next * args.ps_in));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(args.u_in + ((unsigned)(cfg.slot0[i] + q) * s_in + p_next * ps_in)));
         }
         // zero flux above the column top (rainshaft_helpers.jl:80-81); one 64-bit modulo per cell
-        const bool top_level = RAIN && ((p + 1) % cfg.nz == 0);
+        const bool top_level = RAIN && ((p + 1u) % (unsigned)cfg.nz == 0u);
         if constexpr (RAIN) {
             // the sedimentation fluxes of this cell and of the cell above are read at the very end: request them now
             if (live && args.flux != nullptr) {
@@ -851,7 +855,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
 #pragma unroll
                     for (int q = 0; q < 3; ++q)
                         if (q < cfg.nprog[i]) {
-                            const double* fp = args.flux + (cfg.slot0[i] + q) * args.s_flux + p;
+                            const double* fp = args.flux + ((unsigned)(cfg.slot0[i] + q) * s_flux + p);
                             asm volatile("prefetch.global.L1 [%0];" ::"l"(fp));
                             if (!top_level) asm volatile("prefetch.global.L1 [%0];" ::"l"(fp + 1));
                         }
@@ -873,7 +877,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                     double v = cur[i][q];
                     if (RAIN) {
                         v = (v < 0.0) ? 0.0 : v;  // rainshaft_helpers.jl:52
-                        if (args.clip_back != nullptr && live) args.clip_back[(s0 + q) * args.s_clip + p] = v;
+                        if (args.clip_back != nullptr && live) args.clip_back[(unsigned)(s0 + q) * s_clip + p] = v;
                     }
                     raw[i][q] = v;
                     // a zero dividend always takes the ~100-instruction slow path of the FP64 division (13 % of the rainshaft
@@ -911,9 +915,9 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                             unc[k][m] = 0.0; flc[k][m] = 0.0; fuc[k][m] = 0.0;
                             if (m < cfg.nprog[k]) {
                                 const int s = cfg.slot0[k] + m;
-                                flc[k][m] = args.flux[s * args.s_flux + p];
-                                if (!top_level) fuc[k][m] = args.flux[s * args.s_flux + p + 1];
-                                if (with_un) unc[k][m] = args.u_n[s * args.s_n + p];
+                                flc[k][m] = args.flux[(unsigned)s * s_flux + p];
+                                if (!top_level) fuc[k][m] = args.flux[(unsigned)s * s_flux + p + 1u];
+                                if (with_un) unc[k][m] = args.u_n[(unsigned)s * s_n + p];
                             }
                         }
 #pragma unroll
@@ -937,7 +941,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                                     o = (num == 0.0) ? num : div_rn_outofline(num, args.div);  // zero dividend: see the normalisation above
                                     o = (o < 0.0) ? 0.0 : o;
                                 }
-                                args.out[s * args.s_out + p * args.ps_out] = o;
+                                args.out[(unsigned)s * s_out + p * ps_out] = o;
                             }
                 }
                 continue;
@@ -1252,13 +1256,13 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                 unv[k][m] = 0.0; flv[k][m] = 0.0; fluv[k][m] = 0.0;
                 if (m < np && live) {
                     const int s = s0 + m;
-                    if (!args.tend_only && args.u_n != nullptr) unv[k][m] = args.u_n[s * args.s_n + p];
+                    if (!args.tend_only && args.u_n != nullptr) unv[k][m] = args.u_n[(unsigned)s * s_n + p];
                     if (RAIN) {
                         // flux of this cell and of the cell above it, written by flux_kernel.  (Evaluating both inside this kernel was
                         // measured: 0.52 ms instead of 0.42 ms per RHS on C3 — the regime-sorted order separates vertical neighbours,
                         // so every flux would be computed twice, ~1000 instructions each.)
-                        flv[k][m] = args.flux[s * args.s_flux + p];
-                        fluv[k][m] = top_level ? 0.0 : args.flux[s * args.s_flux + p + 1];
+                        flv[k][m] = args.flux[(unsigned)s * s_flux + p];
+                        fluv[k][m] = top_level ? 0.0 : args.flux[(unsigned)s * s_flux + p + 1u];
                     }
                 }
             }
@@ -1291,7 +1295,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                         o = (num == 0.0) ? num : div_rn_outofline(num, args.div);  // zero dividend: see the normalisation above
                         if (RAIN) o = (o < 0.0) ? 0.0 : o;
                     }
-                    args.out[s * args.s_out + p * args.ps_out] = o;
+                    args.out[(unsigned)s * s_out + p * ps_out] = o;
                 }
             }
         }
