@@ -1111,6 +1111,8 @@ struct cloudy_ctx {
     double* d_scratch;     // small device scratch for scalar entry points
     cloudy_state* tmp[3];  // stepper / host-path work buffers
     cloudy_state* flux;    // rainshaft: per-cell sedimentation flux for the thread-per-parcel kernel
+    unsigned long long* d_tile_ctr;  // thread-per-parcel kernel: draw counter of the dynamic tile schedule (tpp_kernel.cuh)
+    unsigned long long tile_base;    // its value once every launch enqueued so far has finished
     int sort_mode;         // regime sort of the parcel order before the thread-per-parcel kernel (0 off, 1 on)
     unsigned char* d_keys;
     int* d_perm;
@@ -1290,6 +1292,9 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
     long long n_blocks = (args.n + TPP_THREADS - 1) / TPP_THREADS;
     long long grid = std::min<long long>(n_blocks, (long long)ctx->sm_count * per_sm);
     if (grid < 1) grid = 1;
+    args.tile_ctr = ctx->d_tile_ctr;
+    args.tile_base = ctx->tile_base;
+    ctx->tile_base += (unsigned long long)((args.n + 31) / 32) + (unsigned long long)grid * (TPP_THREADS / 32);
     void* params[2] = {(void*)&ctx->dev, (void*)&args};
     CUDA_TRY(cudaLaunchKernel((const void*)fn, dim3((unsigned)grid), dim3(TPP_THREADS), params, smem, ctx->stream));
     ctx->launches++;
@@ -1536,6 +1541,9 @@ int cloudy_ctx_create(int device, void* stream, cloudy_ctx** out) {
     CUDA_TRY(cudaMemset(c->d_err, 0, sizeof(unsigned long long)));
     CUDA_TRY(cudaMalloc(&c->d_partial, sizeof(double) * SUM_BLOCKS * MAXSLOT));
     CUDA_TRY(cudaMalloc(&c->d_scratch, sizeof(double) * (CLOUDY_MAX_NODES + 64)));
+    CUDA_TRY(cudaMalloc(&c->d_tile_ctr, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(c->d_tile_ctr, 0, sizeof(unsigned long long)));
+    c->tile_base = 0;
     *out = c;
     return CLOUDY_OK;
 }
@@ -1566,6 +1574,7 @@ int cloudy_ctx_destroy(cloudy_ctx* ctx) {
     cudaFree(ctx->d_err);
     cudaFree(ctx->d_partial);
     cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_tile_ctr);
     cudaFree(ctx->d_stage_aos);
     if (ctx->pipe_ready) {
         for (int i = 0; i < 3; ++i) {
@@ -1669,6 +1678,7 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
     // grid tables
     std::vector<double> tab, tab2;  // tab: SoA tables of the lane-cooperative kernel; tab2: records / rules of the thread-per-parcel kernel
     std::vector<double> tab3, kblk3;  // FixedThreshold thread-per-parcel kernels: aligned records, Taylor degree per node block
+    std::vector<double> ztab;         // FixedThreshold thread-per-parcel kernels: Z-sum polynomials in k (global memory, not staged)
     const int S2 = tpp_rec2_stride(P);
     int mpmax = 0;
     bool any_ln = false;
@@ -1774,10 +1784,12 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
                 d.rec2_off[i] = (int)tab3.size();
                 d.kblk2_off[i] = (int)kblk3.size();
                 const double* r0 = tab2.data() + d.rec_off[i];
+                // weights of the top-order sums carry (x_th - x_j)^(P+1): the kernel adds w'_p1 (g E h)_j and applies θ^-(P+1) once
                 auto push2 = [&](const double* r, bool dummy) {
                     tab3.push_back(r[REC_TMX]);
                     tab3.push_back(r[REC_LSUM]);
-                    for (int p = 0; p < S2 - 2; ++p) tab3.push_back((p <= P && !dummy) ? r[REC_W + p] : 0.0);
+                    const double tp = pow(r[REC_TMX], (double)(P + 1));
+                    for (int p = 0; p < S2 - 2; ++p) tab3.push_back((p <= P && !dummy) ? r[REC_W + p] * tp : 0.0);
                 };
                 for (int c = 0; c < TPP_N_CLASSES; ++c) d.near_cls_end[i][c] = 0;
                 int prev_class = 0;
@@ -1808,6 +1820,65 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
                 d.rec2_far[i] = n_far2;
             }
             mpmax = std::max(mpmax, d.Mp[i]);
+            if (!moving) {
+                // Z[p1][p] = sum_j w_j dx x_j^p1 (g E z^p)_j = exp(e0 + k L) θ^-p G_{p1,p}(k) with the NODE-ONLY functions
+                //   G_{p1,p}(k) = sum_j w_j dx x_j^p1 (x_th - x_j)^p exp(k (ls_j - L)),  ls_j = ln x_j + ln(x_th - x_j),  L = max_j ls_j
+                // (a mixture of decaying exponentials in k with rates <= ~12): tabulated here as degree-7 polynomials on kZtN
+                // intervals of [0, kZtKmax] (interpolation at Chebyshev nodes, evaluated in long double; truncation
+                // (12 h/2)^8 / (8! 2^7) < 1e-16 relative).  The kernel then sums only the top-order terms node by node.
+                const int P1 = P + 1, NZ = P1 * (P1 + 1) / 2;
+                long double Lmax = -INFINITY;
+                for (int j = 0; j < nb; ++j) Lmax = std::max(Lmax, (long double)ell[j] + (long double)lz[j]);
+                d.zt_L[i] = (double)Lmax;
+                std::vector<long double> dj(nb);
+                for (int j = 0; j < nb; ++j) dj[j] = ((long double)ell[j] + (long double)lz[j]) - (long double)d.zt_L[i];
+                std::vector<long double> cw((size_t)NZ * nb);
+                for (int p1 = 0; p1 < P1; ++p1)
+                    for (int pp = p1; pp < P1; ++pp)
+                        for (int j = 0; j < nb; ++j)
+                            cw[(size_t)tri_ct(p1, pp, P1) * nb + j] =
+                                (long double)(w[j] * g_dx * pow(xj[j], (double)p1)) * powl((long double)tmx[j], (long double)pp);
+                // Chebyshev -> monomial conversion matrix for degree 7
+                long double Tm[8][8] = {};
+                Tm[0][0] = 1.0L; Tm[1][1] = 1.0L;
+                for (int m = 1; m < 7; ++m)
+                    for (int c = 0; c < 8; ++c) Tm[m + 1][c] = (c > 0 ? 2.0L * Tm[m][c - 1] : 0.0L) - Tm[m - 1][c];
+                long double tq[8], Tq[8][8];
+                for (int q = 0; q < 8; ++q) {
+                    tq[q] = cosl(3.14159265358979323846264338327950288L * (q + 0.5L) / 8.0L);
+                    for (int m = 0; m < 8; ++m) Tq[q][m] = cosl(m * 3.14159265358979323846264338327950288L * (q + 0.5L) / 8.0L);
+                }
+                const long double hh = (long double)kZtKmax / kZtN;
+                std::vector<long double> ej(nb);
+                std::vector<double>& zt = ztab;
+                d.zt_off[i] = (int)zt.size();
+                zt.resize(zt.size() + (size_t)kZtN * NZ * 8);
+                double* zo = zt.data() + d.zt_off[i];
+                for (int iv = 0; iv < kZtN; ++iv) {
+                    long double fv[8][MAXT];
+                    for (int q = 0; q < 8; ++q) {
+                        const long double kk = (iv + 0.5L * (tq[q] + 1.0L)) * hh;
+                        for (int j = 0; j < nb; ++j) ej[j] = expl(kk * dj[j]);
+                        for (int t = 0; t < NZ; ++t) {
+                            long double acc = 0.0L;
+                            const long double* c = cw.data() + (size_t)t * nb;
+                            for (int j = 0; j < nb; ++j) acc += c[j] * ej[j];
+                            fv[q][t] = acc;
+                        }
+                    }
+                    for (int t = 0; t < NZ; ++t) {
+                        long double a[8], mono[8] = {};
+                        for (int m = 0; m < 8; ++m) {
+                            long double sacc = 0.0L;
+                            for (int q = 0; q < 8; ++q) sacc += fv[q][t] * Tq[q][m];
+                            a[m] = sacc * (m == 0 ? 0.125L : 0.25L);
+                        }
+                        for (int m = 0; m < 8; ++m)
+                            for (int c = 0; c < 8; ++c) mono[c] += a[m] * Tm[m][c];
+                        for (int c = 0; c < 8; ++c) zo[((size_t)iv * NZ + t) * 8 + c] = (double)mono[c];
+                    }
+                }
+            }
         }
     }
     if (any_ln) {
@@ -1849,6 +1920,14 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
             d.xp_off[i] = (int)tab.size();
             tab.resize(tab.size() + kXpN, 0.0);
         }
+    }
+    {
+        while (tab.size() & 15) tab.push_back(0.0);  // 128-byte alignment of the polynomial records (cudaMalloc aligns the base)
+        const int zbase = (int)tab.size();
+        for (int i = 0; i < N; ++i) d.zt_off[i] = (d.quad[i] && !moving) ? d.zt_off[i] + zbase : 0;
+        tab.insert(tab.end(), ztab.begin(), ztab.end());
+        d.zt_inv_h = (double)kZtN / kZtKmax;
+        d.zt_n = kZtN;
     }
     // every check that can still fail comes BEFORE the old configuration is touched: on any error the context keeps
     // its previous, fully valid configuration (tables included)

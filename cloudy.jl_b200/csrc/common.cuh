@@ -18,6 +18,8 @@ constexpr int MAXP = CLOUDY_MAX_P;
 constexpr int MAXM = MAXP + 2;
 constexpr int MAXSLOT = CLOUDY_MAX_SLOTS;
 constexpr int MAXT = MAXM * (MAXM + 1) / 2;  // 28
+constexpr int kZtN = 1024;         // Z-sum tables (cloudy_config_set): intervals of [0, kZtKmax] in k
+constexpr double kZtKmax = 11.0;   // = the largest supported Gamma shape
 
 struct DevConfig {
     int N, P, M, nslots;
@@ -39,6 +41,7 @@ struct DevConfig {
     int tpp2_off, tpp2_total, gl2_off;
     int rec2_off[MAXN], kblk2_off[MAXN];  // per quadrature mode: records (tmx, lsum, w_0..w_P, pad) and Taylor degree per node block
     int rec2_far[MAXN];                   // far nodes padded to a multiple of TPP_NPLF, at least one zero-weight dummy at the end
+    int zt_off[MAXN], zt_n;               // per quadrature mode: Z-sum polynomials in k inside `tab` ([interval][t(p1,p)][8], global memory)
     int near_cls_end[MAXN][5];            // near blocks [0, end[c]) have a Taylor degree class <= c (classes kTaylorClass, tpp_kernel.cuh)
     int n_vel, nz;
     double c[MAXN][MAXN][MAXP][MAXP];
@@ -46,6 +49,7 @@ struct DevConfig {
     double thr[MAXN];
     double norm[MAXSLOT];
     double k_lo, k_hi;
+    double zt_L[MAXN], zt_inv_h;   // Z-sum tables: exponent reference L = max_j ls_j, intervals per unit of k
     double xp_k0, xp_inv_h;
     double velv[CLOUDY_MAX_VEL], velb[CLOUDY_MAX_VEL];  // v*norms[2]^beta, beta
     double gam_b1[CLOUDY_MAX_VEL];                      // Γ(1 + beta): Exponential modes' fractional moment
@@ -72,6 +76,8 @@ struct KArgs {
     const int* perm;      // processing order (regime-sorted parcel indices) or nullptr for identity
     const double* flux;   // rainshaft: per-cell sedimentation flux (SoA like the state), written by flux_kernel
     long long s_flux;
+    unsigned long long* tile_ctr;   // dynamic tile schedule of the thread-per-parcel kernel: global draw counter (never reset) ...
+    unsigned long long tile_base;   // ... and its value when the launch starts (the host advances it by n_tiles + n_warps per launch)
     int presorted;        // host side only: the ensemble is resident in regime order (or must keep its order): no permutation sort
 };
 

@@ -61,31 +61,38 @@ __host__ __device__ constexpr int tri_ct(int p1, int p2, int MP) { return p1 * M
 // is far below anything the sums can resolve.  ~10 FP64 instructions instead of ~20 for the library exp, and only four
 // constants that do not fit an immediate operand.
 constexpr int TPP_EXP_TAB = 256;
-__device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab) {
+template <bool FULL>
+__device__ __forceinline__ double fast_exp_t(double x, const double* __restrict__ tab) {
     const double t = fma(x, 369.3299304675746, 6755399441055744.0);  // 256/ln2, 1.5*2^52
     int n = __double2loint(t);
     const double nf = t - 6755399441055744.0;
-#ifndef TPP_EXP_FULL
-    // accuracy target 2e-13 (parity is asserted at 1e-9; measured worst tendency error against the oracle over 262144
-    // wide-parameter parcels 4.7e-14 of the term scale, 8e-15 with -DTPP_EXP_FULL): one-constant reduction (rounding error
-    // 1.1e-16 |x|, arguments here are within [-745, 60]) and a degree-3 polynomial on |r| <= ln2/512 (truncation r^4/24 <= 1.4e-13).
-    // 7 FP64 instructions instead of 9: -2.8 % on C5.
-    const double r = fma(nf, -0.0027076061740622863, x);   // ln2/256 to 53 bits
-    double p = fma(r, 1.6666666666666666e-01, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-#else
-    double r = fma(nf, -0.002707604318857193, x);   // ln2/256, high 21 bits (nf * hi is exact)
-    r = fma(nf, -1.855205093371747e-09, r);          // ln2/256, low part
-    double p = fma(r, 4.1666666666666664e-02, 1.6666666666666666e-01);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-#endif
+    double p;
+    if constexpr (!FULL) {
+        // accuracy target 2e-13 (parity is asserted at 1e-9; measured worst tendency error against the oracle over 262144
+        // wide-parameter parcels 4.7e-14 of the term scale, 8e-15 with -DTPP_EXP_FULL): one-constant reduction (rounding error
+        // 1.1e-16 |x|, arguments here are within [-745, 60]) and a degree-3 polynomial on |r| <= ln2/512 (truncation r^4/24 <= 1.4e-13).
+        // 7 FP64 instructions instead of 9: -2.8 % on C5.
+        const double r = fma(nf, -0.0027076061740622863, x);   // ln2/256 to 53 bits
+        p = fma(r, 1.6666666666666666e-01, 0.5);
+        p = fma(p, r, 1.0);
+        p = fma(p, r, 1.0);
+    } else {
+        double r = fma(nf, -0.002707604318857193, x);   // ln2/256, high 21 bits (nf * hi is exact)
+        r = fma(nf, -1.855205093371747e-09, r);          // ln2/256, low part
+        p = fma(r, 4.1666666666666664e-02, 1.6666666666666666e-01);
+        p = fma(p, r, 0.5);
+        p = fma(p, r, 1.0);
+        p = fma(p, r, 1.0);
+    }
     p *= tab[n & (TPP_EXP_TAB - 1)];
     n = max(n, -1022 * TPP_EXP_TAB);
     return __hiloint2double(__double2hiint(p) + ((n >> 8) << 20), __double2loint(p));
 }
+#ifndef TPP_EXP_FULL
+__device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab) { return fast_exp_t<false>(x, tab); }
+#else
+__device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab) { return fast_exp_t<true>(x, tab); }
+#endif
 constexpr double kExpOffsetMin = -1.0e6;  // lower clamp of per-parcel exponent offsets fed to fast_exp
 
 // ------------------------------------------------------------------------------------------------
@@ -414,11 +421,12 @@ __device__ __forceinline__ void tpp_cf_nodes(double (&acc)[MP * (MP + 1) / 2], c
     }
 }
 
-// exp + accumulation of one block of NPL nodes (FixedThreshold node loop): y_p = g E z^p, top[p1] += w_p1 y_P z h,
-// Z[p1][p] += w_p1 y_p.  Inlined into the same basic block as the Horner evaluation of h, so that the scheduler interleaves
-// the NPL exponential chains with the NPL Horner chains (the two are independent).
+// exp + accumulation of one block of NPL nodes (FixedThreshold node loop): top[p1] += w'_p1 (g E h)_j with
+// w'_p1 = w_j dx x_j^p1 (x_th - x_j)^(P+1) (the caller applies θ^-(P+1)); the lower-order sums Z[p1][p] do not involve h and come
+// from the k-tables of cloudy_config_set.  Inlined into the same basic block as the Horner evaluation of h, so that the
+// scheduler interleaves the NPL exponential chains with the NPL Horner chains (the two are independent).
 template <int MP, int P, int NPL>
-__device__ __forceinline__ void tpp_block_tail(double (&top)[P + 1], double (&Z)[(P + 1) * (P + 2) / 2], const double2* __restrict__ rb,
+__device__ __forceinline__ void tpp_block_tail(double (&top)[P + 1], const double2* __restrict__ rb,
                                                const double (&z)[NPL], const double (&h)[NPL], const double (&ls)[NPL],
                                                const double k, const double e0, const double cf_lim, const double* __restrict__ exp_tab) {
     constexpr int S2 = tpp_rec2_stride(P);
@@ -427,7 +435,7 @@ __device__ __forceinline__ void tpp_block_tail(double (&top)[P + 1], double (&Z)
     for (int i = 0; i < NPL; ++i) {
         const double gE = fast_exp(fma(k, ls[i], e0), exp_tab);  // g_j * E_j
         const double hs = (z[i] < cf_lim) ? h[i] : 0.0;          // continued-fraction nodes are added by the rare loop (a warp-uniform branch here measured 1 % slower)
-        const double zh = z[i] * hs;
+        const double gh = gE * hs;
         double w[P1 + 1];
 #pragma unroll
         for (int q = 0; q < (S2 - 2) / 2; ++q) {
@@ -435,17 +443,8 @@ __device__ __forceinline__ void tpp_block_tail(double (&top)[P + 1], double (&Z)
             if (2 * q < P1 + 1) w[2 * q] = ww.x;
             if (2 * q + 1 < P1 + 1) w[2 * q + 1] = ww.y;
         }
-        double y[P1];
-        y[0] = gE;
 #pragma unroll
-        for (int p = 1; p < P1; ++p) y[p] = y[p - 1] * z[i];
-        const double ytop = y[P] * zh;
-#pragma unroll
-        for (int p1 = 0; p1 < P1; ++p1) {
-            top[p1] = fma(w[p1], ytop, top[p1]);
-#pragma unroll
-            for (int p = p1; p < P1; ++p) Z[tri_ct(p1, p, P1)] = fma(w[p1], y[p], Z[tri_ct(p1, p, P1)]);
-        }
+        for (int p1 = 0; p1 < P1; ++p1) top[p1] = fma(w[p1], gh, top[p1]);
     }
 }
 
@@ -489,7 +488,8 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
                                                  const double inv_th, const double log_th, const double X, const double poch_top, const double inv_gk,
                                                  const double (&ia)[MP], double* __restrict__ myCt, const int deg,
                                                  const unsigned char* __restrict__ cfdz, const double a_top, const double ser_lim,
-                                                 const double* __restrict__ exp_tab) {
+                                                 const double* __restrict__ exp_tab, const double* __restrict__ ztab, const double zt_inv_h,
+                                                 const int zt_n, const double zt_L) {
     static_assert(MP == P + 2, "all M = P + 2 orders are carried");
     constexpr int T = MP * (MP + 1) / 2;
     constexpr int NPL = tpp_npl(P);
@@ -499,9 +499,16 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
     double top[P1], Z[NZ];
 #pragma unroll
     for (int i = 0; i < P1; ++i) top[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < NZ; ++i) Z[i] = 0.0;
     const double e0 = fmax(fma(-2.0 * k, log_th, -X), kExpOffsetMin);  // exponent offset of g*E
+    // Z[p1][p] = sum_j w_j x_j^p1 (g E z^p)_j = exp(e0 + k L) θ^-p G_{p1,p}(k): the node-only functions G come from the degree-7
+    // polynomials of cloudy_config_set (one 64-byte record per (interval, t), NZ records = a whole number of 128-byte lines per
+    // interval).  The records are requested now (L1 prefetch: no registers) and evaluated after the node loops, where the sums
+    // are needed: nothing of Z is live while the loops run.
+    const double zt_u = k * zt_inv_h;
+    const int zt_iv = min(max((int)zt_u, 0), zt_n - 1);
+    const double2* __restrict__ zr = reinterpret_cast<const double2*>(ztab) + (size_t)zt_iv * (NZ * 4);
+#pragma unroll
+    for (int l = 0; l < (NZ * 64 + 127) / 128; ++l) asm volatile("prefetch.global.L1 [%0];" ::"l"(zr + l * 8));
     const double Xc = fmin(X, ser_lim - 0.5);       // Taylor centre (inside the series regime)
     const double rq = inv_th / Xc;                  // r = z/X_c - 1 = (x_th - x_j) rq - 1
     const bool capped = !(X <= ser_lim - 0.5);      // centre below x_th/θ: r does not vanish at the first nodes
@@ -541,7 +548,7 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
 #pragma unroll
         for (int i = 0; i < TPP_NPLF; ++i) R[i] *= inv_poch;
         if (last) t0 = R[TPP_NPLF - 1];
-        tpp_block_tail<MP, P, TPP_NPLF>(top, Z, rb, z, R, ls, k, e0, cf_lim, exp_tab);
+        tpp_block_tail<MP, P, TPP_NPLF>(top, rb, z, R, ls, k, e0, cf_lim, exp_tab);
     }
     {
         // Taylor coefficients of S about X_c into the parcel's shared-memory column:
@@ -584,7 +591,7 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
                     ls[i] = tl.y;
                 }
                 tpp_taylor_horner<K, NPL, (P < 4)>(h, r, myCt);
-                tpp_block_tail<MP, P, NPL>(top, Z, rb, z, h, ls, k, e0, cf_lim, exp_tab);
+                tpp_block_tail<MP, P, NPL>(top, rb, z, h, ls, k, e0, cf_lim, exp_tab);
             }
         };
         run_class(std::integral_constant<int, tpp_taylor_class(0)>{}, grid.cls_end[0]);
@@ -616,15 +623,41 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
                     for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], r[i], tm);
                 }
             }
-            tpp_block_tail<MP, P, NPL>(top, Z, rb, z, h, ls, k, e0, cf_lim, exp_tab);
+            tpp_block_tail<MP, P, NPL>(top, rb, z, h, ls, k, e0, cf_lim, exp_tab);
         }
+    }
+    {
+        const double tt = fma(2.0, zt_u - (double)zt_iv, -1.0);
+        const double zs0 = fast_exp_t<true>(fma(k, zt_L, e0), exp_tab);
+        double zsc = zs0;
+        double scp[P1];  // the scale θ^-p depends on p only
+#pragma unroll
+        for (int p = 0; p < P1; ++p) { scp[p] = zsc; zsc *= inv_th; }
+#pragma unroll
+        for (int p1 = 0; p1 < P1; ++p1)
+#pragma unroll
+            for (int p = p1; p < P1; ++p) {
+                const int t = tri_ct(p1, p, P1);
+                const double2 c01 = __ldg(zr + t * 4), c23 = __ldg(zr + t * 4 + 1), c45 = __ldg(zr + t * 4 + 2), c67 = __ldg(zr + t * 4 + 3);
+                double g = fma(c67.y, tt, c67.x);
+                g = fma(g, tt, c45.y);
+                g = fma(g, tt, c45.x);
+                g = fma(g, tt, c23.y);
+                g = fma(g, tt, c23.x);
+                g = fma(g, tt, c01.y);
+                g = fma(g, tt, c01.x);
+                Z[t] = g * scp[p];
+            }
     }
     // downward recurrence of the sums; only entries with p1 + p2 <= 2P are ever read by the S terms
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.0;
+    double th_top = inv_th;  // θ^-(P+1): the top weights carry (x_th - x_j)^(P+1)
+#pragma unroll
+    for (int p = 0; p < P; ++p) th_top *= inv_th;
 #pragma unroll
     for (int p1 = 0; p1 < P1; ++p1) {
-        double a = top[p1];
+        double a = top[p1] * th_top;
         if (p1 + (MP - 1) <= 2 * P) acc[tri_ct(p1, MP - 1, MP)] = a;
 #pragma unroll
         for (int p = P; p >= p1; --p) {
@@ -806,7 +839,6 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
     double* myCt = sCt + tid;
 
     const long long n = args.n;
-    const long long stride_all = (long long)gridDim.x * TPP_THREADS;
     // Element offsets are 32-bit unsigned (the host refuses buffers of 2^32 doubles or more, 34 GB each): one IMAD + one
     // IMAD.WIDE per address instead of two 64-bit multiplies (~12 instructions) for each of the ~25 addresses of a parcel
     const unsigned s_in = (unsigned)args.s_in, ps_in = (unsigned)args.ps_in, s_out = (unsigned)args.s_out, ps_out = (unsigned)args.ps_out;
@@ -817,14 +849,23 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
         const unsigned q = (unsigned)((ix < n) ? ix : n - 1);
         return (args.perm != nullptr) ? (unsigned)args.perm[q] : q;
     };
-    unsigned p_next = 0;
-    {
-        const long long b0 = blockIdx.x * (long long)TPP_THREADS + (tid & ~31);
-        if (b0 < n) {
-            p_next = parcel_of(b0);
-        }
-    }
-    for (long long base = blockIdx.x * (long long)TPP_THREADS + (tid & ~31); base < n; base += stride_all) {
+    // Dynamic tile schedule: a tile is 32 consecutive positions of the (regime-sorted) order, and every warp draws its next
+    // tile from a global counter.  With the static round-robin of the earlier versions the kernel lasted as long as its
+    // unluckiest warp (parcel cost varies with the regime; sm__warps_active was 13.5 of 16 on C5).  The counter is never
+    // reset: every warp draws exactly one value beyond the last tile, so a launch advances it by n_tiles + n_warps and the
+    // host passes the value it has at launch (args.tile_base).  Draws run two tiles ahead, so their latency is never waited for.
+    const long long n_tiles = (n + 31) / 32;
+    auto draw = [&]() -> long long {
+        unsigned long long v = 0;
+        if ((tid & 31) == 0) v = atomicAdd(args.tile_ctr, 1ULL) - args.tile_base;
+        return (long long)__shfl_sync(0xffffffffu, v, 0);
+    };
+    long long tile = draw();
+    long long tile_nx = (tile < n_tiles) ? draw() : tile;
+    long long tile_nx2 = tile_nx;
+    unsigned p_next = (tile < n_tiles) ? parcel_of(tile * 32) : 0u;
+    for (; tile < n_tiles; tile = tile_nx, tile_nx = tile_nx2) {
+        const long long base = tile * 32;
         const long long idx = base + (tid & 31);
         const bool live = idx < n;
         const unsigned p = p_next;
@@ -836,8 +877,9 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
 #pragma unroll
             for (int q = 0; q < 3; ++q)
                 cur[i][q] = (q < cfg.nprog[i]) ? args.u_in[(unsigned)(cfg.slot0[i] + q) * s_in + p * ps_in] : 0.0;
-        if (base + stride_all < n) {
-            p_next = parcel_of(base + stride_all);
+        if (tile_nx < n_tiles) {
+            tile_nx2 = draw();
+            p_next = parcel_of(tile_nx * 32);
 #pragma unroll
             for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -1159,7 +1201,8 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                                 fg.n_far = cfg.rec2_far[i];
                                 fg.soa = cfg.tab + cfg.tab_off[i];
                                 fg.nb = cfg.n_bins[i];
-                                tpp_nodes_fixed2<MP, P>(F, fg, k, inv_th, log(th), X, gam_top, inv_gk, ia, myCt, deg, sh.cfdz[ai], a_top, ser_lim, sh.exp32);
+                                tpp_nodes_fixed2<MP, P>(F, fg, k, inv_th, log(th), X, gam_top, inv_gk, ia, myCt, deg, sh.cfdz[ai], a_top, ser_lim, sh.exp32,
+                                                       cfg.tab + cfg.zt_off[i], cfg.zt_inv_h, cfg.zt_n, cfg.zt_L[i]);
                             }
                             double thp[MP];  // H = n^2 θ^{p2}/Γ(k)^2 * sum
                             thp[0] = pre0;
