@@ -1788,7 +1788,7 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
                 auto push2 = [&](const double* r, bool dummy) {
                     tab3.push_back(r[REC_TMX]);
                     tab3.push_back(r[REC_LSUM]);
-                    const double tp = pow(r[REC_TMX], (double)(P + 1));
+                    const double tp = tpp_ztab(P) ? pow(r[REC_TMX], (double)(P + 1)) : 1.0;
                     for (int p = 0; p < S2 - 2; ++p) tab3.push_back((p <= P && !dummy) ? r[REC_W + p] * tp : 0.0);
                 };
                 for (int c = 0; c < TPP_N_CLASSES; ++c) d.near_cls_end[i][c] = 0;
@@ -1820,7 +1820,7 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
                 d.rec2_far[i] = n_far2;
             }
             mpmax = std::max(mpmax, d.Mp[i]);
-            if (!moving) {
+            if (!moving && tpp_ztab(P)) {
                 // Z[p1][p] = sum_j w_j dx x_j^p1 (g E z^p)_j = exp(e0 + k L) θ^-p G_{p1,p}(k) with the NODE-ONLY functions
                 //   G_{p1,p}(k) = sum_j w_j dx x_j^p1 (x_th - x_j)^p exp(k (ls_j - L)),  ls_j = ln x_j + ln(x_th - x_j),  L = max_j ls_j
                 // (a mixture of decaying exponentials in k with rates <= ~12): tabulated here as degree-7 polynomials on kZtN
@@ -1924,7 +1924,7 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
     {
         while (tab.size() & 15) tab.push_back(0.0);  // 128-byte alignment of the polynomial records (cudaMalloc aligns the base)
         const int zbase = (int)tab.size();
-        for (int i = 0; i < N; ++i) d.zt_off[i] = (d.quad[i] && !moving) ? d.zt_off[i] + zbase : 0;
+        for (int i = 0; i < N; ++i) d.zt_off[i] = (d.quad[i] && !moving && tpp_ztab(P)) ? d.zt_off[i] + zbase : 0;
         tab.insert(tab.end(), ztab.begin(), ztab.end());
         d.zt_inv_h = (double)kZtN / kZtKmax;
         d.zt_n = kZtN;

@@ -47,6 +47,10 @@ constexpr int TPP_CT_ROWS_FIXED = 27;
 constexpr int TPP_NPLF = 5;       // far-zone nodes in flight per thread (FixedThreshold): one coefficient product serves five Horner chains
 __host__ __device__ constexpr int tpp_ct_rows(int model) { return model == 2 /*MODEL_BOX_MOVING*/ ? TPP_CT_ROWS : TPP_CT_ROWS_FIXED; }
 constexpr int TPP_TAYLOR_MAX = 26;
+// Lower-order sums Z[p1][p] of the FixedThreshold node loop: from the k-tables of cloudy_config_set (small tensors: 6 records of
+// 64 bytes per parcel and mode) or accumulated node by node (P >= 4: 21 records per parcel and mode overflow the L1 and cost
+// C4 8 % more than the 21 multiply-adds per node they replace — measured)
+__host__ __device__ constexpr bool tpp_ztab(int P) { return P < 4; }
 // FixedThreshold near zone: the node-only Taylor degrees (4..26) are rounded up to five classes; the near blocks are sorted by
 // degree, so each class is a run of consecutive blocks and gets its own loop with a compile-time degree (no per-block dispatch)
 constexpr int TPP_N_CLASSES = 5;
@@ -426,7 +430,7 @@ __device__ __forceinline__ void tpp_cf_nodes(double (&acc)[MP * (MP + 1) / 2], c
 // from the k-tables of cloudy_config_set.  Inlined into the same basic block as the Horner evaluation of h, so that the
 // scheduler interleaves the NPL exponential chains with the NPL Horner chains (the two are independent).
 template <int MP, int P, int NPL>
-__device__ __forceinline__ void tpp_block_tail(double (&top)[P + 1], const double2* __restrict__ rb,
+__device__ __forceinline__ void tpp_block_tail(double (&top)[P + 1], double (&Z)[(P + 1) * (P + 2) / 2], const double2* __restrict__ rb,
                                                const double (&z)[NPL], const double (&h)[NPL], const double (&ls)[NPL],
                                                const double k, const double e0, const double cf_lim, const double* __restrict__ exp_tab) {
     constexpr int S2 = tpp_rec2_stride(P);
@@ -435,7 +439,6 @@ __device__ __forceinline__ void tpp_block_tail(double (&top)[P + 1], const doubl
     for (int i = 0; i < NPL; ++i) {
         const double gE = fast_exp(fma(k, ls[i], e0), exp_tab);  // g_j * E_j
         const double hs = (z[i] < cf_lim) ? h[i] : 0.0;          // continued-fraction nodes are added by the rare loop (a warp-uniform branch here measured 1 % slower)
-        const double gh = gE * hs;
         double w[P1 + 1];
 #pragma unroll
         for (int q = 0; q < (S2 - 2) / 2; ++q) {
@@ -443,8 +446,25 @@ __device__ __forceinline__ void tpp_block_tail(double (&top)[P + 1], const doubl
             if (2 * q < P1 + 1) w[2 * q] = ww.x;
             if (2 * q + 1 < P1 + 1) w[2 * q + 1] = ww.y;
         }
+        if constexpr (tpp_ztab(P)) {
+            const double gh = gE * hs;
 #pragma unroll
-        for (int p1 = 0; p1 < P1; ++p1) top[p1] = fma(w[p1], gh, top[p1]);
+            for (int p1 = 0; p1 < P1; ++p1) top[p1] = fma(w[p1], gh, top[p1]);
+        } else {
+            // y_p = g E z^p, top[p1] += w_p1 y_P z h, Z[p1][p] += w_p1 y_p
+            const double zh = z[i] * hs;
+            double y[P1];
+            y[0] = gE;
+#pragma unroll
+            for (int p = 1; p < P1; ++p) y[p] = y[p - 1] * z[i];
+            const double ytop = y[P] * zh;
+#pragma unroll
+            for (int p1 = 0; p1 < P1; ++p1) {
+                top[p1] = fma(w[p1], ytop, top[p1]);
+#pragma unroll
+                for (int p = p1; p < P1; ++p) Z[tri_ct(p1, p, P1)] = fma(w[p1], y[p], Z[tri_ct(p1, p, P1)]);
+            }
+        }
     }
 }
 
@@ -507,8 +527,13 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
     const double zt_u = k * zt_inv_h;
     const int zt_iv = min(max((int)zt_u, 0), zt_n - 1);
     const double2* __restrict__ zr = reinterpret_cast<const double2*>(ztab) + (size_t)zt_iv * (NZ * 4);
+    if constexpr (tpp_ztab(P)) {
 #pragma unroll
-    for (int l = 0; l < (NZ * 64 + 127) / 128; ++l) asm volatile("prefetch.global.L1 [%0];" ::"l"(zr + l * 8));
+        for (int l = 0; l < (NZ * 64 + 127) / 128; ++l) asm volatile("prefetch.global.L1 [%0];" ::"l"(zr + l * 8));
+    } else {
+#pragma unroll
+        for (int i = 0; i < NZ; ++i) Z[i] = 0.0;
+    }
     const double Xc = fmin(X, ser_lim - 0.5);       // Taylor centre (inside the series regime)
     const double rq = inv_th / Xc;                  // r = z/X_c - 1 = (x_th - x_j) rq - 1
     const bool capped = !(X <= ser_lim - 0.5);      // centre below x_th/θ: r does not vanish at the first nodes
@@ -548,7 +573,7 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
 #pragma unroll
         for (int i = 0; i < TPP_NPLF; ++i) R[i] *= inv_poch;
         if (last) t0 = R[TPP_NPLF - 1];
-        tpp_block_tail<MP, P, TPP_NPLF>(top, rb, z, R, ls, k, e0, cf_lim, exp_tab);
+        tpp_block_tail<MP, P, TPP_NPLF>(top, Z, rb, z, R, ls, k, e0, cf_lim, exp_tab);
     }
     {
         // Taylor coefficients of S about X_c into the parcel's shared-memory column:
@@ -591,7 +616,7 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
                     ls[i] = tl.y;
                 }
                 tpp_taylor_horner<K, NPL, (P < 4)>(h, r, myCt);
-                tpp_block_tail<MP, P, NPL>(top, rb, z, h, ls, k, e0, cf_lim, exp_tab);
+                tpp_block_tail<MP, P, NPL>(top, Z, rb, z, h, ls, k, e0, cf_lim, exp_tab);
             }
         };
         run_class(std::integral_constant<int, tpp_taylor_class(0)>{}, grid.cls_end[0]);
@@ -623,10 +648,10 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
                     for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], r[i], tm);
                 }
             }
-            tpp_block_tail<MP, P, NPL>(top, rb, z, h, ls, k, e0, cf_lim, exp_tab);
+            tpp_block_tail<MP, P, NPL>(top, Z, rb, z, h, ls, k, e0, cf_lim, exp_tab);
         }
     }
-    {
+    if constexpr (tpp_ztab(P)) {
         const double tt = fma(2.0, zt_u - (double)zt_iv, -1.0);
         const double zs0 = fast_exp_t<true>(fma(k, zt_L, e0), exp_tab);
         double zsc = zs0;
@@ -652,9 +677,11 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
     // downward recurrence of the sums; only entries with p1 + p2 <= 2P are ever read by the S terms
 #pragma unroll
     for (int t = 0; t < T; ++t) acc[t] = 0.0;
-    double th_top = inv_th;  // θ^-(P+1): the top weights carry (x_th - x_j)^(P+1)
+    double th_top = 1.0;  // table variant: θ^-(P+1), the top weights carry (x_th - x_j)^(P+1)
+    if constexpr (tpp_ztab(P)) {
 #pragma unroll
-    for (int p = 0; p < P; ++p) th_top *= inv_th;
+        for (int p = 0; p < P + 1; ++p) th_top *= inv_th;
+    }
 #pragma unroll
     for (int p1 = 0; p1 < P1; ++p1) {
         double a = top[p1] * th_top;
@@ -863,9 +890,11 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
     long long tile = draw();
     long long tile_nx = (tile < n_tiles) ? draw() : tile;
     long long tile_nx2 = tile_nx;
-    unsigned p_next = (tile < n_tiles) ? parcel_of(tile * 32) : 0u;
+    unsigned p_next = (tile < n_tiles) ? parcel_of((n_tiles - 1 - tile) * 32) : 0u;
     for (; tile < n_tiles; tile = tile_nx, tile_nx = tile_nx2) {
-        const long long base = tile * 32;
+        // tiles are handed out from the END of the order: the regime sort puts the expensive parcels (continued-fraction regime,
+        // long series) last and the empty cells of a column model first, so the kernel's tail is made of the cheapest tiles
+        const long long base = (n_tiles - 1 - tile) * 32;
         const long long idx = base + (tid & 31);
         const bool live = idx < n;
         const unsigned p = p_next;
@@ -879,7 +908,7 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                 cur[i][q] = (q < cfg.nprog[i]) ? args.u_in[(unsigned)(cfg.slot0[i] + q) * s_in + p * ps_in] : 0.0;
         if (tile_nx < n_tiles) {
             tile_nx2 = draw();
-            p_next = parcel_of(tile_nx * 32);
+            p_next = parcel_of((n_tiles - 1 - tile_nx) * 32);
 #pragma unroll
             for (int i = 0; i < N; ++i)
 #pragma unroll
