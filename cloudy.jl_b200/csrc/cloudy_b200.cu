@@ -1294,7 +1294,10 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
     if (grid < 1) grid = 1;
     args.tile_ctr = ctx->d_tile_ctr;
     args.tile_base = ctx->tile_base;
-    ctx->tile_base += (unsigned long long)((args.n + 31) / 32) + (unsigned long long)grid * (TPP_THREADS / 32);
+    {
+        const int km = (model == CLOUDY_MODEL_RAINSHAFT) ? MODEL_RAINSHAFT : MODEL_BOX;  // the MovingThreshold instances draw like the box ones
+        ctx->tile_base += (unsigned long long)((args.n + tpp_tile(km) - 1) / tpp_tile(km)) + (unsigned long long)grid * tpp_overdraw(km);
+    }
     void* params[2] = {(void*)&ctx->dev, (void*)&args};
     CUDA_TRY(cudaLaunchKernel((const void*)fn, dim3((unsigned)grid), dim3(TPP_THREADS), params, smem, ctx->stream));
     ctx->launches++;

@@ -19,7 +19,10 @@
 
 namespace cloudy {
 
-constexpr int TPP_THREADS = 128;
+#ifndef TPP_THREADS_N
+#define TPP_THREADS_N 128
+#endif
+constexpr int TPP_THREADS = TPP_THREADS_N;
 // nodes in flight per thread (measured on C2, P = 2: 2 → 0.70 ms, 3 → 0.66, 4 → 0.74, 5 → 0.73); high-order tensors carry
 // up to 28 accumulators per node set, so they keep fewer nodes in flight
 #ifndef TPP_NPL_LARGE
@@ -38,7 +41,7 @@ __host__ __device__ constexpr int tpp_npl(int P) { return P >= 4 ? TPP_NPL_LARGE
 #define TPP_MINB_LARGE 2
 #endif
 __host__ __device__ constexpr int tpp_min_blocks(int N, int P, int model) {
-    return model == MODEL_BOX_MOVING ? 2 : ((N * P <= 4 && N <= 3) ? TPP_MINB_SMALL : TPP_MINB_LARGE);
+    return (model == MODEL_BOX_MOVING ? 2 : ((N * P <= 4 && N <= 3) ? TPP_MINB_SMALL : TPP_MINB_LARGE)) * 128 / TPP_THREADS;
 }
 constexpr int TPP_CT_ROWS = 64;  // MovingThreshold instances: series coefficients c_0..c_63 (the Taylor coefficients overwrite them)
 // FixedThreshold instances keep only the Taylor coefficients t_0..t_26 in shared memory (the far-zone series runs on
@@ -47,6 +50,11 @@ constexpr int TPP_CT_ROWS_FIXED = 27;
 constexpr int TPP_NPLF = 5;       // far-zone nodes in flight per thread (FixedThreshold): one coefficient product serves five Horner chains
 __host__ __device__ constexpr int tpp_ct_rows(int model) { return model == 2 /*MODEL_BOX_MOVING*/ ? TPP_CT_ROWS : TPP_CT_ROWS_FIXED; }
 constexpr int TPP_TAYLOR_MAX = 26;
+// dynamic tile schedule (tpp_kernel, launch_tpp): box instances draw one TPP_THREADS-parcel tile per block and iteration,
+// column instances one 32-parcel tile per warp; every drawer draws once beyond the last tile
+__host__ __device__ constexpr bool tpp_block_sync(int model) { return model != 1 /*MODEL_RAINSHAFT*/; }
+__host__ __device__ constexpr int tpp_tile(int model) { return tpp_block_sync(model) ? TPP_THREADS : 32; }
+__host__ __device__ constexpr int tpp_overdraw(int model) { return tpp_block_sync(model) ? 1 : TPP_THREADS / 32; }
 // Lower-order sums Z[p1][p] of the FixedThreshold node loop: from the k-tables of cloudy_config_set (small tensors: 6 records of
 // 64 bytes per parcel and mode) or accumulated node by node (P >= 4: 21 records per parcel and mode overflow the L1 and cost
 // C4 8 % more than the 21 multiply-adds per node they replace — measured)
@@ -876,25 +884,58 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
         const unsigned q = (unsigned)((ix < n) ? ix : n - 1);
         return (args.perm != nullptr) ? (unsigned)args.perm[q] : q;
     };
-    // Dynamic tile schedule: a tile is 32 consecutive positions of the (regime-sorted) order, and every warp draws its next
-    // tile from a global counter.  With the static round-robin of the earlier versions the kernel lasted as long as its
-    // unluckiest warp (parcel cost varies with the regime; sm__warps_active was 13.5 of 16 on C5).  The counter is never
-    // reset: every warp draws exactly one value beyond the last tile, so a launch advances it by n_tiles + n_warps and the
-    // host passes the value it has at launch (args.tile_base).  Draws run two tiles ahead, so their latency is never waited for.
-    const long long n_tiles = (n + 31) / 32;
-    auto draw = [&]() -> long long {
-        unsigned long long v = 0;
-        if ((tid & 31) == 0) v = atomicAdd(args.tile_ctr, 1ULL) - args.tile_base;
-        return (long long)__shfl_sync(0xffffffffu, v, 0);
+    // Dynamic tile schedule: tiles are consecutive positions of the (regime-sorted) order, drawn from a global counter.  With
+    // the static round-robin of the earlier versions the kernel lasted as long as its unluckiest warp (parcel cost varies with
+    // the regime; sm__warps_active was 13.5 of 16 on C5).  The counter is never reset: every drawer draws exactly one value
+    // beyond the last tile, so a launch advances it by n_tiles + n_drawers and the host passes the value it has at launch
+    // (args.tile_base).  Draws run two tiles ahead, so their latency is never waited for.
+    //   Box instances (BSYNC): a tile is TPP_THREADS positions, drawn by thread 0 and published through shared memory at the
+    // barrier that opens every iteration, so the four warps of a block walk through the kernel's code together and share
+    // instruction-cache lines (with independent warps instruction fetch was 25 % of the stall samples on C5: 2.72 -> 2.58 ms).
+    //   Column instances: a tile is one warp's 32 positions and every warp draws for itself — a block there often holds warps
+    // of empty cells next to warps of cloudy ones, which a barrier would chain together (measured: 0.74 -> 0.78 ms per C3 step).
+    constexpr bool BSYNC = tpp_block_sync(MODEL);
+    constexpr int TILE = tpp_tile(MODEL);
+    __shared__ long long s_tile[2];
+    const long long n_tiles = (n + TILE - 1) / TILE;
+    auto draw1 = [&]() -> long long { return (long long)(atomicAdd(args.tile_ctr, 1ULL) - args.tile_base); };
+    auto draw = [&]() -> long long {  // warp-level draw
+        long long v = 0;
+        if ((tid & 31) == 0) v = draw1();
+        return __shfl_sync(0xffffffffu, v, 0);
     };
-    long long tile = draw();
-    long long tile_nx = (tile < n_tiles) ? draw() : tile;
-    long long tile_nx2 = tile_nx;
-    unsigned p_next = (tile < n_tiles) ? parcel_of((n_tiles - 1 - tile) * 32) : 0u;
-    for (; tile < n_tiles; tile = tile_nx, tile_nx = tile_nx2) {
-        // tiles are handed out from the END of the order: the regime sort puts the expensive parcels (continued-fraction regime,
-        // long series) last and the empty cells of a column model first, so the kernel's tail is made of the cheapest tiles
-        const long long base = (n_tiles - 1 - tile) * 32;
+    // tiles are handed out from the END of the order: the regime sort puts the expensive parcels (continued-fraction regime,
+    // long series) last and the empty cells of a column model first, so the kernel's tail is made of the cheapest tiles
+    auto tile_pos = [&](long long t) -> long long { return (n_tiles - 1 - t) * TILE + (BSYNC ? (tid & ~31) : 0); };
+    long long tile, tile_nx, tile_nx2;  // BSYNC: tile_nx2 is thread 0's draw in flight
+    int it = 0;
+    if constexpr (BSYNC) {
+        if (tid == 0) s_tile[0] = draw1();
+        __syncthreads();
+        tile = s_tile[0];
+        tile_nx = tile;
+        tile_nx2 = tile;
+        if (tid == 0 && tile < n_tiles) tile_nx2 = draw1();
+    } else {
+        tile = draw();
+        tile_nx = (tile < n_tiles) ? draw() : tile;
+        tile_nx2 = tile_nx;
+    }
+    unsigned p_next = (tile < n_tiles) ? parcel_of(tile_pos(tile)) : 0u;
+    for (; tile < n_tiles; tile = tile_nx, tile_nx = (BSYNC ? tile_nx : tile_nx2)) {
+        const long long base = tile_pos(tile);
+        bool draw_more;
+        if constexpr (BSYNC) {
+            if (tid == 0) s_tile[(it + 1) & 1] = tile_nx2;
+            __syncthreads();
+            tile_nx = s_tile[(it + 1) & 1];
+            ++it;
+            draw_more = tile_nx < n_tiles;
+            if (tid == 0 && draw_more) tile_nx2 = draw1();
+        } else {
+            draw_more = tile_nx < n_tiles;
+            if (draw_more) tile_nx2 = draw();
+        }
         const long long idx = base + (tid & 31);
         const bool live = idx < n;
         const unsigned p = p_next;
@@ -906,9 +947,8 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
 #pragma unroll
             for (int q = 0; q < 3; ++q)
                 cur[i][q] = (q < cfg.nprog[i]) ? args.u_in[(unsigned)(cfg.slot0[i] + q) * s_in + p * ps_in] : 0.0;
-        if (tile_nx < n_tiles) {
-            tile_nx2 = draw();
-            p_next = parcel_of((n_tiles - 1 - tile_nx) * 32);
+        if (draw_more) {
+            p_next = parcel_of(tile_pos(tile_nx));
 #pragma unroll
             for (int i = 0; i < N; ++i)
 #pragma unroll
