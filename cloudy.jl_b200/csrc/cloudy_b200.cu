@@ -1294,12 +1294,13 @@ static int launch_tpp(cloudy_ctx* ctx, tpp_fn fn, int model, KArgs args) {
     if (grid < 1) grid = 1;
     args.tile_ctr = ctx->d_tile_ctr;
     args.tile_base = ctx->tile_base;
+    void* params[2] = {(void*)&ctx->dev, (void*)&args};
+    CUDA_TRY(cudaLaunchKernel((const void*)fn, dim3((unsigned)grid), dim3(TPP_THREADS), params, smem, ctx->stream));
     {
+        // the launch is enqueued: it will advance the draw counter by one draw per tile plus one overdraw per drawer
         const int km = (model == CLOUDY_MODEL_RAINSHAFT) ? MODEL_RAINSHAFT : MODEL_BOX;  // the MovingThreshold instances draw like the box ones
         ctx->tile_base += (unsigned long long)((args.n + tpp_tile(km) - 1) / tpp_tile(km)) + (unsigned long long)grid * tpp_overdraw(km);
     }
-    void* params[2] = {(void*)&ctx->dev, (void*)&args};
-    CUDA_TRY(cudaLaunchKernel((const void*)fn, dim3((unsigned)grid), dim3(TPP_THREADS), params, smem, ctx->stream));
     ctx->launches++;
     return CLOUDY_OK;
 }
@@ -2644,8 +2645,12 @@ int cloudy_get_coal_ints_1(cloudy_ctx* ctx, const double* params, double* out) {
     if ((rc = ensure_tmp(ctx, 0, 1))) return rc;
     if ((rc = ensure_tmp(ctx, 1, 1))) return rc;
     double h[MAXSLOT];
-    for (int i = 0; i < d.N; ++i)
+    for (int i = 0; i < d.N; ++i) {
+        // given distributions bypass update_dist_from_moments' clamp: the shape must lie inside the incomplete-gamma and Z-sum tables
+        if (d.quad[i] && d.kind[i] == CLOUDY_GAMMA && d.nprog[i] > 2 && !(params[3 * i + 2] > 0.0 && params[3 * i + 2] <= kZtKmax))
+            return fail(CLOUDY_ERR_UNSUPPORTED, "Gamma shape parameter outside (0, 11]: outside the incomplete-gamma tables");
         for (int q = 0; q < d.nprog[i]; ++q) h[d.slot0[i] + q] = params[3 * i + q];
+    }
     if ((rc = cloudy_state_upload(ctx, ctx->tmp[0], h, 1))) return rc;
     KArgs a = base_args(ctx, ctx->tmp[0], ctx->tmp[1]);
     a.tend_only = 1;

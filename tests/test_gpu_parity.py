@@ -504,3 +504,62 @@ def test_wide_parameter_sweep(cb):
     n2 = np.full(kk.size, 0.1); th2 = np.full(kk.size, 5.0)
     state = np.concatenate([m1, np.stack([n2, n2 * th2], axis=1)], axis=1) * np.array([1e6, 1e-3, 1e-12, 1e6, 1e-3])
     _check_box(cb, par, state, kk.size, lanes=(0, 1, 8))
+
+
+def test_dynamic_tile_schedule_sizes_and_repeats(cb):
+    """The thread-per-parcel kernel draws its tiles from a device counter that is never reset (tpp_kernel.cuh): every ensemble
+    size around the tile and block boundaries, launched back to back on one context, must reproduce the same per-parcel
+    results bit for bit, and agree with the lane-cooperative kernel (an independent implementation with a static schedule)."""
+    from cloudy_b200 import workloads as W
+    par, state = W.c2_gamma_exp(n_parcels=5000)
+    model = cb.CoalescenceModel(par)
+    model.ctx.set_lanes(8)
+    ref = model.coal_tendency_host(state)
+    model.ctx.set_lanes(1)
+    full = model.coal_tendency_host(state)
+    scale = np.abs(ref).max(axis=0)
+    assert np.all(np.abs(full - ref) <= 1e-10 * scale)
+    for rep in range(3):
+        for n in (1, 2, 31, 32, 33, 127, 128, 129, 255, 257, 1023, 4096, 4097, 5000):
+            got = model.coal_tendency_host(state[:n])
+            assert np.array_equal(got, full[:n]), (rep, n)
+    model.ctx.set_lanes(0)
+
+
+def test_z_sum_tables_against_node_by_node_sums(cb):
+    """Small tensors take the lower-order sums Z[p1][p] from polynomial tables in the Gamma shape k (cloudy_config_set); the
+    lane-cooperative kernel sums the same terms node by node.  Shapes over the whole clamp range, including both ends."""
+    from cloudy_b200 import workloads as W
+    from cloudy_b200.workloads import _moments_from_params, _norm_factors, NORMS
+    from cloudy_b200 import _lib as L
+    par, _ = W.c2_gamma_exp(n_parcels=8)
+    rng = np.random.default_rng(77)
+    n = 4096
+    k1 = np.concatenate([np.linspace(1e-3, 10.0, n - 6), [1e-6, 1e-4, 9.999, 10.0, 10.0, 0.5]])
+    n1 = np.exp(rng.uniform(math.log(1e1), math.log(1e3), n)); th1 = np.exp(rng.uniform(math.log(0.01), math.log(1.0), n))
+    n2 = np.exp(rng.uniform(math.log(1e-6), 0.0, n)); th2 = np.exp(rng.uniform(0.0, math.log(30.0), n))
+    m = np.concatenate([_moments_from_params(L.GAMMA, n1, th1, k1, 3), _moments_from_params(L.EXPONENTIAL, n2, th2, None, 2)], axis=1)
+    state = m * _norm_factors((3, 2), NORMS)
+    model = cb.CoalescenceModel(par)
+    model.ctx.set_lanes(8)
+    ref = model.coal_tendency_host(state)
+    model.ctx.set_lanes(1)
+    got = model.coal_tendency_host(state)
+    model.ctx.set_lanes(0)
+    opar = oracle_params(par)
+    worst = 0.0
+    for i in list(range(0, n, 97)) + list(range(n - 6, n)):
+        r, sc = O.rhs_coal(state[i], opar, return_scale=True)
+        ok, w = tendency_close(got[i], r, sc, RTOL)
+        assert ok, (i, k1[i], w)
+        ok2, w2 = tendency_close(got[i], ref[i], sc, 1e-11)  # the two kernels share the rule: two orders tighter
+        assert ok2, (i, k1[i], w2)
+        worst = max(worst, w2)
+
+
+def test_given_gamma_shape_outside_the_tables_is_refused(cb):
+    dist = (cb.GammaPrimitiveParticleDistribution(100.0, 0.1, 12.0), cb.ExponentialPrimitiveParticleDistribution(1.0, 1.0))
+    kernel = cb.CoalescenceTensor(np.array([[0.0, 5e-3], [5e-3, 0.0]]))
+    coal_data = cb.CoalescenceData(kernel, (3, 2), (0.5, math.inf))
+    with pytest.raises(Exception, match="shape parameter"):
+        cb.get_coal_ints(cb.AnalyticalCoalStyle(), dist, coal_data)
