@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(256, 4) flux_kernel(const __grid_constant__ De
                 if (q >= np) break;
                 double v = raw[i][q];
                 v = (v < 0.0) ? 0.0 : v;  // rainshaft_helpers.jl:52
-                mn[q] = v / cfg.norm[s0 + q];
+                mn[q] = norm_div(v, cfg.norm[s0 + q], cfg.inv_norm[s0 + q]);
             }
             const ModeParams mp = params_from_moments(kind, mn[0], mn[1], mn[2], kind == CLOUDY_GAMMA ? cfg.k_lo : -INFINITY,
                                                       kind == CLOUDY_GAMMA ? cfg.k_hi : INFINITY);
@@ -1649,6 +1649,7 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
         for (int q = 0; q < np; ++q) {
             d.slot_mode[slot] = i; d.slot_order[slot] = q;
             d.norm[slot] = cfg->norms[0] * pow(cfg->norms[1], (double)q);  // helper_functions.jl:49
+            d.inv_norm[slot] = 1.0 / d.norm[slot];
             ++slot;
         }
     }
@@ -1856,12 +1857,13 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
                 std::vector<long double> ej(nb);
                 std::vector<double>& zt = ztab;
                 d.zt_off[i] = (int)zt.size();
-                zt.resize(zt.size() + (size_t)kZtN * NZ * 8);
+                zt.resize(zt.size() + (size_t)kZtN * (NZ + 1) * 8);  // per interval: NZ sums, then 1/Γ(k+1)
                 double* zo = zt.data() + d.zt_off[i];
                 for (int iv = 0; iv < kZtN; ++iv) {
-                    long double fv[8][MAXT];
+                    long double fv[8][MAXT + 1];
                     for (int q = 0; q < 8; ++q) {
                         const long double kk = (iv + 0.5L * (tq[q] + 1.0L)) * hh;
+                        fv[q][NZ] = 1.0L / tgammal(kk + 1.0L);
                         for (int j = 0; j < nb; ++j) ej[j] = expl(kk * dj[j]);
                         for (int t = 0; t < NZ; ++t) {
                             long double acc = 0.0L;
@@ -1870,7 +1872,7 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
                             fv[q][t] = acc;
                         }
                     }
-                    for (int t = 0; t < NZ; ++t) {
+                    for (int t = 0; t < NZ + 1; ++t) {
                         long double a[8], mono[8] = {};
                         for (int m = 0; m < 8; ++m) {
                             long double sacc = 0.0L;
@@ -1879,7 +1881,7 @@ int cloudy_config_set(cloudy_ctx* ctx, const cloudy_config* cfg) {
                         }
                         for (int m = 0; m < 8; ++m)
                             for (int c = 0; c < 8; ++c) mono[c] += a[m] * Tm[m][c];
-                        for (int c = 0; c < 8; ++c) zo[((size_t)iv * NZ + t) * 8 + c] = (double)mono[c];
+                        for (int c = 0; c < 8; ++c) zo[((size_t)iv * (NZ + 1) + t) * 8 + c] = (double)mono[c];
                     }
                 }
             }

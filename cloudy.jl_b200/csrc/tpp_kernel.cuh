@@ -513,11 +513,11 @@ struct FixedGrid {
 // downward recurrence runs ONCE per parcel after the loop instead of once per node.
 template <int MP, int P>
 __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2], const FixedGrid grid, const double k,
-                                                 const double inv_th, const double log_th, const double X, const double poch_top, const double inv_gk,
+                                                 const double inv_th, const double log_th, const double X, const double poch_top, double& inv_gk,
                                                  const double (&ia)[MP], double* __restrict__ myCt, const int deg,
                                                  const unsigned char* __restrict__ cfdz, const double a_top, const double ser_lim,
                                                  const double* __restrict__ exp_tab, const double* __restrict__ ztab, const double zt_inv_h,
-                                                 const int zt_n, const double zt_L) {
+                                                 const int zt_n, const double zt_L, const bool gamma_mode) {
     static_assert(MP == P + 2, "all M = P + 2 orders are carried");
     constexpr int T = MP * (MP + 1) / 2;
     constexpr int NPL = tpp_npl(P);
@@ -534,10 +534,10 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
     // are needed: nothing of Z is live while the loops run.
     const double zt_u = k * zt_inv_h;
     const int zt_iv = min(max((int)zt_u, 0), zt_n - 1);
-    const double2* __restrict__ zr = reinterpret_cast<const double2*>(ztab) + (size_t)zt_iv * (NZ * 4);
+    const double2* __restrict__ zr = reinterpret_cast<const double2*>(ztab) + (size_t)zt_iv * ((NZ + 1) * 4);  // NZ sums + 1/Γ(k+1)
     if constexpr (tpp_ztab(P)) {
 #pragma unroll
-        for (int l = 0; l < (NZ * 64 + 127) / 128; ++l) asm volatile("prefetch.global.L1 [%0];" ::"l"(zr + l * 8));
+        for (int l = 0; l < ((NZ + 1) * 64 + 127) / 128; ++l) asm volatile("prefetch.global.L1 [%0];" ::"l"(zr + l * 8));
     } else {
 #pragma unroll
         for (int i = 0; i < NZ; ++i) Z[i] = 0.0;
@@ -681,6 +681,19 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
                 g = fma(g, tt, c01.x);
                 Z[t] = g * scp[p];
             }
+        if (gamma_mode) {
+            // 1/Γ(k) = k / Γ(k+1) from the same record set (entry NZ tabulates the entire function 1/Γ(k+1)): replaces the
+            // log + exp + Stirling tail of gamma_shape_inv (~150 instructions per parcel); needed only from here on
+            const double2 c01 = __ldg(zr + NZ * 4), c23 = __ldg(zr + NZ * 4 + 1), c45 = __ldg(zr + NZ * 4 + 2), c67 = __ldg(zr + NZ * 4 + 3);
+            double g = fma(c67.y, tt, c67.x);
+            g = fma(g, tt, c45.y);
+            g = fma(g, tt, c45.x);
+            g = fma(g, tt, c23.y);
+            g = fma(g, tt, c23.x);
+            g = fma(g, tt, c01.y);
+            g = fma(g, tt, c01.x);
+            inv_gk = k * g;
+        }
     }
     // downward recurrence of the sums; only entries with p1 + p2 <= 2P are ever read by the S terms
 #pragma unroll
@@ -991,9 +1004,9 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                         if (args.clip_back != nullptr && live) args.clip_back[(unsigned)(s0 + q) * s_clip + p] = v;
                     }
                     raw[i][q] = v;
-                    // a zero dividend always takes the ~100-instruction slow path of the FP64 division (13 % of the rainshaft
-                    // instance's executed instructions: 61 % of the C3 cells are exact zeros); 0/norm = 0 with v's sign
-                    mnv[i][q] = (v == 0.0) ? v : v / cfg.norm[s0 + q];
+                    // (an inline IEEE division sends every zero dividend through its ~100-instruction slow path: 13 % of the
+                    // rainshaft instance's executed instructions when 61 % of the C3 cells are exact zeros)
+                    mnv[i][q] = norm_div(v, cfg.norm[s0 + q], cfg.inv_norm[s0 + q]);
                     if (RAIN) cell_empty = cell_empty && (mnv[i][q] < kEps);  // rainshaft_helpers.jl:67
                 }
             }
@@ -1132,7 +1145,8 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                     } else {
                         const double inv_th = 1.0 / th;
                         // Gamma(k): the MovingThreshold instances need it itself (inverse incomplete gamma), the others only 1/Gamma(k)
-                        const double inv_gk = MOVING ? 1.0 : ((cfg.kind[i] == CLOUDY_GAMMA) ? gamma_shape_inv(k) : 1.0);
+                        // (the FixedThreshold instances of small tensors read 1/Γ(k) from the Z-sum records after the node loops)
+                        double inv_gk = (MOVING || tpp_ztab(P)) ? 1.0 : ((cfg.kind[i] == CLOUDY_GAMMA) ? gamma_shape_inv(k) : 1.0);
                         const double gk = MOVING ? ((cfg.kind[i] == CLOUDY_GAMMA) ? gamma_shape(k) : 1.0) : 1.0;
                         // All M orders are carried even when N_2d_ints[i] = M - 1 (two adjacent 2-moment modes): the downward
                         // recurrence from the higher top order gives the same lower orders, the unused top entries are masked in
@@ -1196,7 +1210,6 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                             else myCt[0] = cc;
                             for (int nn = deg + 1; nn <= deg_w; ++nn) myCt[nn * TPP_THREADS] = 0.0;
                         }
-                        const double pre0 = MOVING ? nmd * nmd / (gk * gk) : (nmd * inv_gk) * (nmd * inv_gk);
                         auto finish = [&](auto mp_tag) {
                             constexpr int MP = decltype(mp_tag)::value;
                             // ia[p] = 1/(k+p) for p < MP-1 from ONE division (prefix and suffix products; k >= eps keeps the product
@@ -1271,10 +1284,10 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
                                 fg.soa = cfg.tab + cfg.tab_off[i];
                                 fg.nb = cfg.n_bins[i];
                                 tpp_nodes_fixed2<MP, P>(F, fg, k, inv_th, log(th), X, gam_top, inv_gk, ia, myCt, deg, sh.cfdz[ai], a_top, ser_lim, sh.exp32,
-                                                       cfg.tab + cfg.zt_off[i], cfg.zt_inv_h, cfg.zt_n, cfg.zt_L[i]);
+                                                       cfg.tab + cfg.zt_off[i], cfg.zt_inv_h, cfg.zt_n, cfg.zt_L[i], cfg.kind[i] == CLOUDY_GAMMA);
                             }
                             double thp[MP];  // H = n^2 θ^{p2}/Γ(k)^2 * sum
-                            thp[0] = pre0;
+                            thp[0] = MOVING ? nmd * nmd / (gk * gk) : (nmd * inv_gk) * (nmd * inv_gk);
 #pragma unroll
                             for (int pp = 1; pp < MP; ++pp) thp[pp] = thp[pp - 1] * th;
                             contract(mp_tag, F, thp);
