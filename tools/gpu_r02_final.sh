@@ -17,8 +17,10 @@ $NCU --set full -k regex:flux_kernel -s 160 -c 1 -o $O/r02_prof_flux -f python t
 python tools/ncu_summary.py $O/r02_prof_flux.ncu-rep 10 > $O/r02_flux_kernel_c3_ncu_full_summary.txt 2>&1
 rm -f $O/r02_prof_flux.ncu-rep
 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "test_c2_gamma_exp or test_c3_rainshaft_rhs or ragged" > $O/r02_compute_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?" >> $O/r02_compute_sanitizer_memcheck.log
+compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "ragged" > $O/r02_compute_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?" >> $O/r02_compute_sanitizer_racecheck.log
 tail -12 $O/r02_final_bench.log | cut -c1-400
 cat $O/r02_bench_other_configs_n1.jsonl | cut -c1-330
 cat $O/r02_launches_c3_rainshaft_summary.csv
 grep "duration\|fp64_cycles\|issue_active" $O/r02_tpp_kernel_c4_ncu_full_summary.txt $O/r02_tpp_kernel_c3_rainshaft_ncu_full_summary.txt $O/r02_tpp_kernel_c5_ncu_full_summary.txt $O/r02_flux_kernel_c3_ncu_full_summary.txt
 tail -4 $O/r02_compute_sanitizer_memcheck.log
+tail -4 $O/r02_compute_sanitizer_racecheck.log
