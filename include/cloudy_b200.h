@@ -20,7 +20,10 @@
  *  - host buffers are array-of-structures, parcel-major: host[p*n_slots + s] (one reference
  *    moment vector after another), unless stated otherwise;
  *  - a context is bound to one CUDA device and one stream and is not re-entrant;
- *  - compute calls enqueue on the context's stream and return; cloudy_sync() blocks.
+ *  - compute calls enqueue on the context's stream and return; cloudy_sync() blocks;
+ *  - limits: Gamma shape parameters in (0, 11] (the reference clamps k to (eps, 10], ParticleDistributions.jl:459); an ensemble
+ *    buffer (stride x n_slots) must stay below 2^32 doubles per device (the kernels form 32-bit element offsets): calls that
+ *    exceed either return CLOUDY_ERR_UNSUPPORTED.
  */
 #ifndef CLOUDY_B200_H
 #define CLOUDY_B200_H
@@ -207,6 +210,7 @@ int cloudy_moment_source_helper(cloudy_ctx* ctx, int32_t kind, const double* par
 int cloudy_compute_threshold(cloudy_ctx* ctx, int32_t kind, const double* params, double percentile, double minx, double* out);
 /* get_coal_ints(AnalyticalCoalStyle(), pdists, coal_data[, MovingThreshold()]) for ONE set of distributions;
  * params: [n_modes][3]; out: Σ nprog doubles (normalised units, exactly the reference's return value).
+ * Given distributions bypass update_dist_from_moments' clamp: a Gamma shape outside (0, 11] is refused (CLOUDY_ERR_UNSUPPORTED).
  * Coalescence.jl:115-185 */
 int cloudy_get_coal_ints_1(cloudy_ctx* ctx, const double* params, double* out);
 /* get_sedimentation_flux(pdists, vel) for ONE set of distributions, vel given explicitly. Sedimentation.jl:22-37 */
