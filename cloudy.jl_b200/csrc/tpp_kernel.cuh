@@ -935,6 +935,15 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
         tile_nx2 = tile_nx;
     }
     unsigned p_next = (tile < n_tiles) ? parcel_of(tile_pos(tile)) : 0u;
+    // next parcel's moments held in registers across the node loops: the 128-register box instances of small tensors (-0.7 % on
+    // C5; the column instance spills 48 bytes with it and measured 0.72 instead of 0.69 ms per C3 step)
+    constexpr bool REGPF = tpp_ztab(P) && tpp_min_blocks(N, P, MODEL) * TPP_THREADS >= 512 && !RAIN;
+    double nxt[N][3];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            nxt[i][q] = (REGPF && tile < n_tiles && q < cfg.nprog[i]) ? args.u_in[(unsigned)(cfg.slot0[i] + q) * s_in + p_next * ps_in] : 0.0;
     for (; tile < n_tiles; tile = tile_nx, tile_nx = (BSYNC ? tile_nx : tile_nx2)) {
         const long long base = tile_pos(tile);
         bool draw_more;
@@ -953,21 +962,26 @@ __global__ void __launch_bounds__(TPP_THREADS, tpp_min_blocks(N, P, MODEL)) tpp_
         const bool live = idx < n;
         const unsigned p = p_next;
         double cur[N][3];
-        // this parcel's moments (requested one iteration ago with an L2 prefetch: holding the NEXT parcel's values in registers
-        // across the node loops made the 128-register instances spill them, and the spill store waits for the DRAM load)
+        // this parcel's moments.  REGPF instances hold the NEXT parcel's values in registers across the node loops (possible since
+        // the Z sums left the loops: 0 spill bytes); the others request them one iteration ahead with an L2 prefetch (holding
+        // them in registers made those instances spill them, and the spill store waits for the DRAM load)
 #pragma unroll
         for (int i = 0; i < N; ++i)
 #pragma unroll
-            for (int q = 0; q < 3; ++q)
-                cur[i][q] = (q < cfg.nprog[i]) ? args.u_in[(unsigned)(cfg.slot0[i] + q) * s_in + p * ps_in] : 0.0;
+            for (int q = 0; q < 3; ++q) {
+                if constexpr (REGPF) cur[i][q] = nxt[i][q];
+                else cur[i][q] = (q < cfg.nprog[i]) ? args.u_in[(unsigned)(cfg.slot0[i] + q) * s_in + p * ps_in] : 0.0;
+            }
         if (draw_more) {
             p_next = parcel_of(tile_pos(tile_nx));
 #pragma unroll
             for (int i = 0; i < N; ++i)
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
-                    if (q < cfg.nprog[i])
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(args.u_in + ((unsigned)(cfg.slot0[i] + q) * s_in + p_next * ps_in)));
+                    if (q < cfg.nprog[i]) {
+                        if constexpr (REGPF) nxt[i][q] = args.u_in[(unsigned)(cfg.slot0[i] + q) * s_in + p_next * ps_in];
+                        else asm volatile("prefetch.global.L2 [%0];" ::"l"(args.u_in + ((unsigned)(cfg.slot0[i] + q) * s_in + p_next * ps_in)));
+                    }
         }
         // zero flux above the column top (rainshaft_helpers.jl:80-81); one 64-bit modulo per cell
         const bool top_level = RAIN && ((p + 1u) % (unsigned)cfg.nz == 0u);
