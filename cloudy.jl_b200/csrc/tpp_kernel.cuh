@@ -11,8 +11,9 @@
 // node tables are shared-memory broadcasts; the only per-thread table is the parcel's series coefficients
 // c_n = 1/(a)_{n+1} (column `tid` of a [64][threads] shared array, conflict-free).  NPL nodes are in flight
 // per thread: their Horner chains share each coefficient load and hide the DFMA latency.
-// Warps are made homogeneous (similar series length, same series/continued-fraction regime) by an optional
-// regime sort of the parcel order (args.perm).
+// Warps are made homogeneous (similar series length, same series/continued-fraction regime) by the regime order of
+// the ensemble (data sort of resident box ensembles, permutation args.perm for column states), and the work is handed
+// out in tiles drawn from a device counter (see the parcel loop of tpp_kernel).
 #pragma once
 #include <type_traits>
 #include "common.cuh"
