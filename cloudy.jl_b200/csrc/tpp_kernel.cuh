@@ -647,14 +647,23 @@ __device__ __forceinline__ void tpp_nodes_fixed2(double (&acc)[MP * (MP + 1) / 2
                 h[i] = 0.0;
             }
             const int Kown = capped ? TPP_TAYLOR_MAX : Kj;
+            // a block whose nodes lie beyond the series limit in every parcel of the warp (threshold deep in the tail: the
+            // near nodes sit at z ~ x_th/θ) is evaluated by the continued-fraction loop alone; its Taylor values would be
+            // discarded by the select in tpp_block_tail (h stays 0: bit-identical)
+            double zmin = z[0];
+#pragma unroll
+            for (int i = 1; i < NPL; ++i) zmin = fmin(zmin, z[i]);
+            const bool all_cf = __all_sync(0xffffffffu, !(zmin < cf_lim));
             // unrolled for the high-order tensors only: rolled, this loop costs C4 (a quarter of its parcels is capped) 40 %;
             // unrolled, its code costs C5 (no capped parcel) 2 % through the instruction cache
+            if (!all_cf) {
 #pragma unroll CAP_UNROLL
-            for (int m = TPP_TAYLOR_MAX; m >= 0; --m) {
-                const double tm = myCt[m * TPP_THREADS];
-                if (m <= Kown) {
+                for (int m = TPP_TAYLOR_MAX; m >= 0; --m) {
+                    const double tm = myCt[m * TPP_THREADS];
+                    if (m <= Kown) {
 #pragma unroll
-                    for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], r[i], tm);
+                        for (int i = 0; i < NPL; ++i) h[i] = fma(h[i], r[i], tm);
+                    }
                 }
             }
             tpp_block_tail<MP, P, NPL>(top, Z, rb, z, h, ls, k, e0, cf_lim, exp_tab);
